@@ -1,0 +1,211 @@
+// Shared device helpers: element types, vector load/store, epilogue description.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+typedef __half f16;
+
+// ---------------------------------------------------------------------------------------
+// element conversion
+// ---------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<f16>(f16 v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ f16 from_f<f16>(float v) { return __float2half_rn(v); }
+
+__device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
+  __nv_bfloat162 t = __halves2bfloat162(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack2(f16 a, f16 b) {
+  __half2 t = __halves2half2(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// load NV consecutive elements as float; pointer must be aligned to NV*sizeof(T) when
+// NV*sizeof(T) is 8 or 16 bytes (all call sites guarantee it: leading dims are multiples of 8).
+template <typename T, int NV> __device__ __forceinline__ void load_vec(const T* __restrict__ p, float* v) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (NV % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        float4 t = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = to_f<T>(p[i]);
+    }
+  } else {
+    if constexpr (NV % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 8; ++i) {
+        uint4 t = reinterpret_cast<const uint4*>(p)[i];
+        const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * i + j] = to_f<T>(e[j]);
+      }
+    } else if constexpr (NV % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        uint2 t = reinterpret_cast<const uint2*>(p)[i];
+        const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[4 * i + j] = to_f<T>(e[j]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = to_f<T>(p[i]);
+    }
+  }
+}
+
+template <typename T, int NV> __device__ __forceinline__ void store_vec(T* __restrict__ p, const float* v) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (NV % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i)
+        reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) p[i] = from_f<T>(v[i]);
+    }
+  } else {
+    if constexpr (NV % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 8; ++i) {
+        uint4 t;
+        t.x = pack2(from_f<T>(v[8 * i + 0]), from_f<T>(v[8 * i + 1]));
+        t.y = pack2(from_f<T>(v[8 * i + 2]), from_f<T>(v[8 * i + 3]));
+        t.z = pack2(from_f<T>(v[8 * i + 4]), from_f<T>(v[8 * i + 5]));
+        t.w = pack2(from_f<T>(v[8 * i + 6]), from_f<T>(v[8 * i + 7]));
+        reinterpret_cast<uint4*>(p)[i] = t;
+      }
+    } else if constexpr (NV % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        uint2 t;
+        t.x = pack2(from_f<T>(v[4 * i + 0]), from_f<T>(v[4 * i + 1]));
+        t.y = pack2(from_f<T>(v[4 * i + 2]), from_f<T>(v[4 * i + 3]));
+        reinterpret_cast<uint2*>(p)[i] = t;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) p[i] = from_f<T>(v[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// GEMM / conv epilogue description (shared by the CUDA-core and tcgen05 kernels)
+// ---------------------------------------------------------------------------------------
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GEGLU = 3, ACT_HEAD = 4, ACT_SIGMOID = 5 };
+enum { MAP_LINEAR = 0, MAP_TOKENS = 1, MAP_PIXSHUF = 2 };
+
+struct Epi {
+  void* out;             // primary output, element (orow, ocol) at out[orow*ldo + ocol]
+  void* out_relu;        // optional copy relu(value) in the activation dtype, same indexing
+  const float* bias;     // [N] or null
+  const float* rowbias;  // table [(m / rb_div) % rb_mod][rb_ld] or null
+  const void* res1;      // optional residual, indexed like out (ld_res)
+  const void* res2;
+  const float* head_w;   // ACT_HEAD: 1x1 conv weights [N] and bias (dpt.py:121-123)
+  long long ldo, ld_res1, ld_res2, rb_ld;
+  int rb_div, rb_mod;
+  int out_f32, res1_f32, res2_f32;  // 1: that tensor is float32 regardless of T
+  int act;
+  int map;
+  int map_p;       // MAP_TOKENS: patches per frame
+  int ps_k, ps_h, ps_w, ps_c;  // MAP_PIXSHUF: k, grid h, grid w, channels per tap (padded)
+  float head_b;
+  float sig_sign;  // ACT_SIGMOID: sigmoid(sig_sign * x)
+};
+
+// maps GEMM row m -> output row for the column-independent mappings
+__device__ __forceinline__ long long epi_row(const Epi& e, long long m) {
+  if (e.map == MAP_TOKENS) return m + m / e.map_p + 1;
+  return m;
+}
+
+// Apply the epilogue to NV consecutive columns [n0, n0+NV) of GEMM row m and store.
+// `orow` is the output row for MAP_LINEAR/MAP_TOKENS (conv kernels pass their own pixel row).
+template <typename T, int NV>
+__device__ __forceinline__ void epi_apply(const Epi& e, long long m, long long orow, int n0, float* v) {
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + n0 + i);
+  }
+  if (e.rowbias) {
+    const float* rb = e.rowbias + (long long)((m / e.rb_div) % e.rb_mod) * e.rb_ld + n0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __ldg(rb + i);
+  }
+  if (e.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = gelu_erf(v[i]);
+  }
+  long long ocol = n0;
+  if (e.map == MAP_PIXSHUF) {
+    // m = (f, y, x) over the ps_h x ps_w grid; n = (ky*k + kx)*ps_c + c
+    int tap = n0 / e.ps_c;
+    ocol = n0 - tap * e.ps_c;
+    int ky = tap / e.ps_k, kx = tap - ky * e.ps_k;
+    long long hw = (long long)e.ps_h * e.ps_w;
+    long long f = m / hw;
+    int r = (int)(m - f * hw);
+    int y = r / e.ps_w, x = r - y * e.ps_w;
+    orow = (f * (e.ps_h * e.ps_k) + (long long)y * e.ps_k + ky) * ((long long)e.ps_w * e.ps_k) + (long long)x * e.ps_k + kx;
+  }
+  if (e.res1) {
+    float r[NV];
+    if (e.res1_f32) load_vec<float, NV>((const float*)e.res1 + orow * e.ld_res1 + ocol, r);
+    else load_vec<T, NV>((const T*)e.res1 + orow * e.ld_res1 + ocol, r);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += r[i];
+  }
+  if (e.res2) {
+    float r[NV];
+    if (e.res2_f32) load_vec<float, NV>((const float*)e.res2 + orow * e.ld_res2 + ocol, r);
+    else load_vec<T, NV>((const T*)e.res2 + orow * e.ld_res2 + ocol, r);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += r[i];
+  }
+  if (e.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (e.act == ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 1.f / (1.f + __expf(-e.sig_sign * v[i]));
+  }
+  if (e.out) {
+    if (e.out_f32) store_vec<float, NV>((float*)e.out + orow * e.ldo + ocol, v);
+    else store_vec<T, NV>((T*)e.out + orow * e.ldo + ocol, v);
+  }
+  if (e.out_relu) {
+    float r[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r[i] = fmaxf(v[i], 0.f);
+    store_vec<T, NV>((T*)e.out_relu + orow * e.ldo + ocol, r);
+  }
+}

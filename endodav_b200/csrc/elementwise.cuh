@@ -1,0 +1,349 @@
+// Memory-bound kernels of the EndoDAV forward: preprocessing, normalisations, resampling.
+// All activations are NHWC / token-major; T is the activation dtype (float, bf16, f16).
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// K1: resize (bilinear, align_corners=True) + ImageNet normalise + im2col for the 14x14
+// patch embedding.  Replaces endodav.py:153,155 and the unfold implied by
+// patch_embed.py:75-77.  Output A0[(f*P + py*pw + px), Kp] with k = c*196 + ky*14 + kx
+// (the flatten order of the conv weight), zero padded to Kp.
+// ---------------------------------------------------------------------------------------
+template <typename T, bool U8>
+__global__ void preprocess_patches_kernel(const void* __restrict__ src, T* __restrict__ out, int F, int H, int W,
+                                          int h, int w, int Kp) {
+  const int ph = h / 14, pw = w / 14;
+  const long long total = (long long)F * ph * pw * Kp;
+  const float sy = (h > 1) ? (float)(H - 1) / (float)(h - 1) : 0.f;
+  const float sx = (w > 1) ? (float)(W - 1) / (float)(w - 1) : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % Kp);
+    long long row = i / Kp;
+    float val = 0.f;
+    if (k < 588) {
+      int c = k / 196, r = k - c * 196;
+      int ky = r / 14, kx = r - ky * 14;
+      int px = (int)(row % pw);
+      long long t = row / pw;
+      int py = (int)(t % ph);
+      int f = (int)(t / ph);
+      int y = py * 14 + ky, x = px * 14 + kx;
+      float v;
+      if (U8) {
+        // uint8 HWC frames already at network resolution (infer_video_depth path)
+        const uint8_t* s = (const uint8_t*)src;
+        v = (float)s[(((long long)f * H + y) * W + x) * 3 + c] / 255.0f;
+      } else {
+        const float* s = (const float*)src + ((long long)f * 3 + c) * H * W;
+        if (H == h && W == w) {
+          v = s[(long long)y * W + x];
+        } else {
+          // area_pixel_compute_source_index with align_corners=True
+          float fy = sy * y, fx = sx * x;
+          int y0 = (int)fy, x0 = (int)fx;
+          int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+          float ly = fy - y0, lx = fx - x0;
+          float v00 = s[(long long)y0 * W + x0], v01 = s[(long long)y0 * W + x1];
+          float v10 = s[(long long)y1 * W + x0], v11 = s[(long long)y1 * W + x1];
+          v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+        }
+      }
+      const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+      const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+      val = (v - mean) / stdv;
+    }
+    out[i] = from_f<T>(val);
+  }
+}
+
+// cls row of every frame: x[f, 0, :] = cls_token + pos_embed[0]  (vision_transformer.py:225-227)
+__global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ cls_row, int F, int N, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F * D) return;
+  int f = i / D, d = i - f * D;
+  x[(long long)f * N * D + d] = cls_row[d];
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over D (one warp per row), float32 in -> T out.  With grp>0 the input is
+// [.., grp rows] per frame and the first `skip` rows of every frame are dropped from the
+// (compact) output: the final norm on the four taps + cls split
+// (vision_transformer.py:318-321).  Two-pass statistics in registers.
+// ---------------------------------------------------------------------------------------
+template <typename TOut, int MAXV>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, TOut* __restrict__ out, long long Mout, int D,
+                                 float eps, int grp, int skip) {
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= Mout) return;
+  long long mo = warp, mi = mo;
+  if (grp > 0) {
+    int per = grp - skip;
+    mi = (mo / per) * grp + skip + (mo % per);
+  }
+  const float* xr = x + mi * D;
+  float v[MAXV * 4];
+  float s = 0.f;
+#pragma unroll
+  for (int it = 0; it < MAXV; ++it) {
+    int c = (it * 32 + lane) * 4;
+    if (c < D) {
+      float4 t = *reinterpret_cast<const float4*>(xr + c);
+      v[4 * it] = t.x; v[4 * it + 1] = t.y; v[4 * it + 2] = t.z; v[4 * it + 3] = t.w;
+      s += t.x + t.y + t.z + t.w;
+    } else {
+      v[4 * it] = v[4 * it + 1] = v[4 * it + 2] = v[4 * it + 3] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int it = 0; it < MAXV; ++it) {
+    int c = (it * 32 + lane) * 4;
+    if (c < D) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float d = v[4 * it + j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  TOut* orow = out + mo * D;
+#pragma unroll
+  for (int it = 0; it < MAXV; ++it) {
+    int c = (it * 32 + lane) * 4;
+    if (c < D) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = (v[4 * it + j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+      store_vec<TOut, 4>(orow + c, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm(32) statistics per (frame, group) over (C/32) x hw elements, NHWC input.
+// Two passes (mean, then centred variance); the second pass hits L2.  stats[f*32+g] = {mean, rstd}
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void groupnorm_stats_kernel(const T* __restrict__ x, float2* __restrict__ stats, int hw, int C, float eps) {
+  const int f = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / 32;
+  const T* base = x + (long long)f * hw * C + g * cpg;
+  __shared__ float red[32];
+  __shared__ float s_mean;
+  const int total = hw * cpg;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int p = i / cpg, c = i - p * cpg;
+    s += to_f<T>(base[(long long)p * C + c]);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) s_mean = t / (float)total;
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int p = i / cpg, c = i - p * cpg;
+    float d = to_f<T>(base[(long long)p * C + c]) - mean;
+    q += d * d;
+  }
+  q = warp_sum(q);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) stats[f * 32 + g] = make_float2(mean, rsqrtf(t / (float)total + eps));
+  }
+}
+
+template <typename T>
+__global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __restrict__ stats,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       T* __restrict__ y, long long total8, int hw, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  long long e0 = i * 8;
+  int c0 = (int)(e0 % C);
+  int f = (int)(e0 / ((long long)hw * C));
+  const int cpg = C / 32;
+  float v[8];
+  load_vec<T, 8>(x + e0, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = c0 + j;
+    float2 st = stats[f * 32 + c / cpg];
+    v[j] = (v[j] - st.x) * st.y * __ldg(gamma + c) + __ldg(beta + c);
+  }
+  store_vec<T, 8>(y + e0, v);
+}
+
+// ---------------------------------------------------------------------------------------
+// Bilinear resize, align_corners=True, NHWC, 8 channels per thread.
+// (util/blocks.py:156-158; dpt_pyramid.py:90-92)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, int F, int h, int w, int oh, int ow,
+                                     int C) {
+  const int c8 = C / 8;
+  const long long total = (long long)F * oh * ow * c8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % c8) * 8;
+  long long p = i / c8;
+  int ox = (int)(p % ow);
+  long long t = p / ow;
+  int oy = (int)(t % oh);
+  int f = (int)(t / oh);
+  const float sy = (oh > 1) ? (float)(h - 1) / (float)(oh - 1) : 0.f;
+  const float sx = (ow > 1) ? (float)(w - 1) / (float)(ow - 1) : 0.f;
+  float fy = sy * oy, fx = sx * ox;
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  float ly = fy - y0, lx = fx - x0;
+  const T* b = x + (long long)f * h * w * C + c;
+  float a[8], bq[8], cq[8], d[8], o[8];
+  load_vec<T, 8>(b + ((long long)y0 * w + x0) * C, a);
+  load_vec<T, 8>(b + ((long long)y0 * w + x1) * C, bq);
+  load_vec<T, 8>(b + ((long long)y1 * w + x0) * C, cq);
+  load_vec<T, 8>(b + ((long long)y1 * w + x1) * C, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * bq[j]) + ly * ((1.f - lx) * cq[j] + lx * d[j]);
+  store_vec<T, 8>(y + p * C + c, o);
+}
+
+// single-channel float32 bilinear resize (align_corners=True): disparity pyramid
+// (dpt_pyramid.py:95-97) and the final per-window resize (endodav.py:205).
+__global__ void resize_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int F, int h, int w, int oh,
+                                  int ow, int sigmoid) {
+  const long long total = (long long)F * oh * ow;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int ox = (int)(i % ow);
+  long long t = i / ow;
+  int oy = (int)(t % oh);
+  int f = (int)(t / oh);
+  const float sy = (oh > 1) ? (float)(h - 1) / (float)(oh - 1) : 0.f;
+  const float sx = (ow > 1) ? (float)(w - 1) / (float)(ow - 1) : 0.f;
+  float fy = sy * oy, fx = sx * ox;
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  float ly = fy - y0, lx = fx - x0;
+  const float* b = x + (long long)f * h * w;
+  float v = (1.f - ly) * ((1.f - lx) * b[(long long)y0 * w + x0] + lx * b[(long long)y0 * w + x1]) +
+            ly * ((1.f - lx) * b[(long long)y1 * w + x0] + lx * b[(long long)y1 * w + x1]);
+  if (sigmoid) v = 1.f / (1.f + expf(-v));
+  y[i] = v;
+}
+
+__global__ void sigmoid_inplace_kernel(float* __restrict__ x, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = 1.f / (1.f + expf(-x[i]));
+}
+
+// explicit im2col for the single stride-2 3x3 conv (resize_layers[3], dpt.py:85-90):
+// out[(f,oy,ox), (ky,kx,c)] with zero padding 1.
+template <typename T>
+__global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ out, int F, int H, int W, int C, int OH,
+                                 int OW, int stride) {
+  const int c8 = C / 8;
+  const long long total = (long long)F * OH * OW * 9 * c8;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % c8) * 8;
+  long long t = i / c8;
+  int tap = (int)(t % 9);
+  long long p = t / 9;
+  int ox = (int)(p % OW);
+  long long t2 = p / OW;
+  int oy = (int)(t2 % OH);
+  int f = (int)(t2 / OH);
+  int ky = tap / 3, kx = tap - ky * 3;
+  int iy = oy * stride + ky - 1, ix = ox * stride + kx - 1;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W) load_vec<T, 8>(x + (((long long)f * H + iy) * W + ix) * C + c, v);
+  store_vec<T, 8>(out + (p * 9 + tap) * C + c, v);
+}
+
+// copy T -> float32 (debug taps)
+template <typename T>
+__global__ void to_f32_kernel(const T* __restrict__ x, float* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = to_f<T>(x[i]);
+}
+
+// strided channel copy NHWC [.., Cs] -> [.., Cd] (first min(Cs,Cd) channels), debug taps of padded maps
+template <typename T>
+__global__ void copy_channels_f32_kernel(const T* __restrict__ x, float* __restrict__ y, long long rows, int Cs, int Cd) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Cd) return;
+  long long r = i / Cd;
+  int c = (int)(i - r * Cd);
+  y[i] = to_f<T>(x[r * Cs + c]);
+}
+
+// channels-first LayerNorm of ResBottleneckBlock on NHWC rows (layers/utils.py:171-179),
+// optional exact GELU, one warp per pixel; in/out dtype T.  Rows hold C (padded) channels of
+// which the first Cr are real; padded outputs are written as zero.
+template <typename T>
+__global__ void rowln_act_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 T* __restrict__ y, long long M, int C, int Cr, float eps, int gelu) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const T* xr = x + warp * C;
+  float s = 0.f;
+  for (int c = lane; c < Cr; c += 32) s += to_f<T>(xr[c]);
+  const float mean = warp_sum(s) / (float)Cr;
+  float q = 0.f;
+  for (int c = lane; c < Cr; c += 32) { float d = to_f<T>(xr[c]) - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)Cr + eps);
+  for (int c = lane; c < C; c += 32) {
+    float v = 0.f;
+    if (c < Cr) {
+      v = (to_f<T>(xr[c]) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      if (gelu) v = gelu_erf(v);
+    }
+    y[warp * C + c] = from_f<T>(v);
+  }
+}
+
+// x[f, 1+p, :] += LN_cf(r[f*P+p, :])   -- the residual-block add into patch tokens (block.py:146-150)
+template <typename T>
+__global__ void resblock_add_kernel(float* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, long long Mp, int P, int D, float eps) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= Mp) return;
+  const T* rr = r + warp * D;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += to_f<T>(rr[c]);
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int c = lane; c < D; c += 32) { float d = to_f<T>(rr[c]) - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+  float* xr = x + (warp + warp / P + 1) * D;
+  for (int c = lane; c < D; c += 32)
+    xr[c] += (to_f<T>(rr[c]) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+}
+
+// compact copy of the patch tokens of the fp32 residual stream into T (drops cls rows)
+template <typename T>
+__global__ void tokens_to_patches_kernel(const float* __restrict__ x, T* __restrict__ y, long long Mp, int P, int D) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = Mp * (D / 4);
+  if (i >= total) return;
+  long long r = i / (D / 4);
+  int c = (int)(i - r * (D / 4)) * 4;
+  float v[4];
+  load_vec<float, 4>(x + (r + r / P + 1) * D + c, v);
+  store_vec<T, 4>(y + r * D + c, v);
+}

@@ -1,0 +1,823 @@
+// endodav_b200 engine: context, weight registry, shape plan and the forward graph of
+// endodav.forward (models/endodav/endodav.py:150-160) expressed as a fixed sequence of
+// sm_100a kernel launches on the caller's stream.  C ABI in include/endodav_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ops.cuh"
+
+using namespace edv;
+
+namespace {
+
+std::string g_create_error;
+
+struct WeightRef {
+  const void* ptr;
+  size_t bytes;
+};
+
+struct Buf {
+  size_t off = 0;
+  size_t bytes = 0;
+};
+
+struct DebugTap {
+  Buf buf;            // float32 snapshot
+  long long rows = 0;
+  int cols = 0;
+};
+
+struct MMPlan {
+  int C = 0, h = 0, w = 0;
+};
+
+struct Plan {
+  bool valid = false;
+  int B = 0, T = 0, H = 0, W = 0, h = 0, w = 0;
+  int BT = 0, ph = 0, pw = 0, P = 0, N = 0;
+  long long M = 0, Mp = 0;
+  int ph2 = 0, pw2 = 0;
+  int Cp[4] = {0, 0, 0, 0};
+  int out_h[4] = {0, 0, 0, 0}, out_w[4] = {0, 0, 0, 0};
+  MMPlan mm[4];
+  size_t total = 0;
+  std::map<std::string, Buf> bufs;
+  std::map<std::string, DebugTap> taps;
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct edv_ctx {
+  edv_config cfg;
+  std::unordered_map<std::string, WeightRef> weights;
+  Plan plan;
+  std::string err;
+  int last_launches = 0;
+  int debug = 0;
+  int Kp = 640;
+};
+
+namespace {
+
+const int KPATCH = 640;  // 3*14*14 = 588 padded to a multiple of 64
+
+struct Fwd {
+  edv_ctx* c;
+  Launch L;
+  unsigned char* ws;
+  int dt, eng;
+  size_t es;  // element size of the activation dtype
+
+  Fwd(edv_ctx* ctx, void* workspace, cudaStream_t s) : c(ctx), ws((unsigned char*)workspace) {
+    L.stream = s;
+    dt = ctx->cfg.dtype;
+    eng = ctx->cfg.dtype == EDV_F32 ? EDV_ENGINE_SIMT : ctx->cfg.engine;
+    es = dtype_size(dt);
+  }
+  bool tc() const { return eng == EDV_ENGINE_TC; }
+
+  void* buf(const char* name) {
+    auto it = c->plan.bufs.find(name);
+    if (it == c->plan.bufs.end()) {
+      L.fail(EDV_ERR_STATE, std::string("internal: unknown buffer ") + name);
+      return ws;
+    }
+    return ws + it->second.off;
+  }
+  const void* w(const std::string& name, size_t min_bytes = 0) {
+    auto it = c->weights.find(name);
+    if (it == c->weights.end()) {
+      L.fail(EDV_ERR_WEIGHT, "missing packed weight '" + name + "'");
+      return nullptr;
+    }
+    if (min_bytes && it->second.bytes < min_bytes) {
+      char b[64];
+      snprintf(b, sizeof b, " (%zu < %zu bytes)", it->second.bytes, min_bytes);
+      L.fail(EDV_ERR_WEIGHT, "packed weight '" + name + "' too small" + b);
+      return nullptr;
+    }
+    return it->second.ptr;
+  }
+  const float* wf(const std::string& name, size_t n) { return (const float*)w(name, n * 4); }
+  const void* wt(const std::string& name, size_t n) { return w(name, n * es); }
+
+  // ---- building blocks --------------------------------------------------------------------
+  void linear(const void* A, long long M, int K, const std::string& wname, int N, Epi e) {
+    GemmArgs a;
+    a.A = A; a.W = wt(wname, (size_t)N * K); a.M = (int)M; a.N = N; a.K = K; a.lda = K; a.e = e;
+    if (!L.ok()) return;
+    gemm(L, dt, eng, a);
+  }
+  void conv3(const void* X, int F, int H, int Wd, int C, const std::string& wname, int N, Epi e) {
+    GemmArgs a;
+    a.A = X; a.W = wt(wname, (size_t)N * 9 * C); a.M = F * H * Wd; a.N = N; a.K = 9 * C; a.e = e;
+    a.conv = true; a.F = F; a.H = H; a.Wd = Wd; a.C = C; a.stride = 1;
+    if (!L.ok()) return;
+    gemm(L, dt, eng, a);
+  }
+  Epi ep(void* out, long long ldo, const float* bias) {
+    Epi e = epi_zero();
+    e.out = out; e.ldo = ldo; e.bias = bias;
+    return e;
+  }
+  void snapshot(const char* name, const void* src, bool src_f32, long long rows, int cols_src, int cols) {
+    if (!c->debug || !L.ok()) return;
+    auto it = c->plan.taps.find(name);
+    if (it == c->plan.taps.end()) return;
+    float* dst = (float*)(ws + it->second.buf.off);
+    long long n = rows * cols;
+    if (src_f32) copy_channels_f32_kernel<float><<<nblk(n, 256), 256, 0, L.stream>>>((const float*)src, dst, rows, cols_src, cols);
+    else EDV_DISPATCH_T(dt, { copy_channels_f32_kernel<T><<<nblk(n, 256), 256, 0, L.stream>>>((const T*)src, dst, rows, cols_src, cols); });
+    L.check("debug snapshot");
+  }
+
+  // TemporalModule (motion_module.py:60-65,102-126,164-177): X [BT*hw, C] NHWC -> Y same
+  void motion(int j, const void* X, void* Y) {
+    const Plan& p = c->plan;
+    const int C = p.mm[j].C, hw = p.mm[j].h * p.mm[j].w, T = p.T, B = p.B;
+    const long long Mm = (long long)p.BT * hw;
+    const std::string n = "mm" + std::to_string(j) + ".";
+    void* gnb = buf("mm.gn");
+    float* hs = (float*)buf("mm.hs");
+    void* lnb = buf("mm.ln");
+    void* qkvb = buf("mm.qkv");
+    void* att = buf("mm.att");
+    void* gg = buf("mm.gg");
+    void* hsT = buf("mm.hsT");
+    groupnorm(L, dt, X, wf(n + "gn.w", C), wf(n + "gn.b", C), gnb, (float2*)buf("mm.stats"), p.BT, hw, C, 1e-6f);
+    {
+      Epi e = ep(hs, C, wf(n + "pin.b", C));
+      e.out_f32 = 1;
+      linear(gnb, Mm, C, n + "pin.w", C, e);
+    }
+    for (int a = 0; a < 2; ++a) {
+      const std::string an = n + "a" + std::to_string(a) + ".";
+      layernorm(L, dt, hs, wf(an + "ln.w", C), wf(an + "ln.b", C), lnb, Mm, C, 1e-5f);
+      {
+        // q|k|v in one GEMM; (x + pe) W = x W + pe W -> per-frame additive table
+        Epi e = ep(qkvb, 3 * C, nullptr);
+        if (!c->cfg.rope) {
+          e.rowbias = wf(an + "petab", (size_t)T * 3 * C);
+          e.rb_div = hw; e.rb_mod = T; e.rb_ld = 3 * C;
+        }
+        linear(lnb, Mm, C, an + "qkv.w", 3 * C, e);
+      }
+      temporal_attention(L, dt, qkvb, att, B, T, hw, C);
+      {
+        Epi e = ep(hs, C, wf(an + "out.b", C));
+        e.out_f32 = 1; e.res1 = hs; e.res1_f32 = 1; e.ld_res1 = C;
+        linear(att, Mm, C, an + "out.w", C, e);
+      }
+    }
+    layernorm(L, dt, hs, wf(n + "ffln.w", C), wf(n + "ffln.b", C), lnb, Mm, C, 1e-5f);
+    if (tc()) {
+      Epi e = ep(gg, 4 * C, wf(n + "geglu.b", 8 * C));
+      e.act = ACT_GEGLU;
+      linear(lnb, Mm, C, n + "geglu.w", 8 * C, e);
+    } else {
+      void* tmp = buf("mm.gg2");
+      linear(lnb, Mm, C, n + "geglu.w", 8 * C, ep(tmp, 8 * C, wf(n + "geglu.b", 8 * C)));
+      if (L.ok()) {
+        long long tot = Mm * 4 * C;
+        EDV_DISPATCH_T(dt, { geglu_pair_kernel<T><<<nblk(tot, 256), 256, 0, L.stream>>>((const T*)tmp, (T*)gg, Mm, 4 * C); });
+        L.check("geglu");
+      }
+    }
+    {
+      Epi e = ep(hsT, C, wf(n + "ff2.b", C));
+      e.res1 = hs; e.res1_f32 = 1; e.ld_res1 = C;
+      linear(gg, Mm, 4 * C, n + "ff2.w", C, e);
+    }
+    {
+      Epi e = ep(Y, C, wf(n + "pout.b", C));
+      e.res1 = X; e.ld_res1 = C;
+      linear(hsT, Mm, C, n + "pout.w", C, e);
+    }
+  }
+
+  // ResidualConvUnit (util/blocks.py:78-91): out = conv2(relu(conv1(relu(x)))) + x (+ extra)
+  //   xr = relu(x) (written by x's producer), out_relu optionally receives relu(out)
+  void rcu(const std::string& n, const void* x, const void* xr, const void* extra, void* out, void* out_relu, int F_,
+           int H, int Wd, int C, void* tmp) {
+    Epi e1 = ep(tmp, C, wf(n + "c1.b", C));
+    e1.act = ACT_RELU;
+    conv3(xr, F_, H, Wd, C, n + "c1.w", C, e1);
+    Epi e2 = ep(out, C, wf(n + "c2.b", C));
+    e2.res1 = x; e2.ld_res1 = C;
+    if (extra) { e2.res2 = extra; e2.ld_res2 = C; }
+    e2.out_relu = out_relu;
+    conv3(tmp, F_, H, Wd, C, n + "c2.w", C, e2);
+  }
+
+  // FeatureFusionBlock (util/blocks.py:134-162).  out_conv (1x1, linear) commutes with the
+  // bilinear resize, so it runs at the low resolution first (4x fewer FLOPs).
+  //   x0 : main input (raw); x0r = relu(x0) needed only when x1 == nullptr
+  //   x1 / x1r : skip input and its relu copy (nullable)
+  void fusion(int k, const void* x0, const void* x0r, const void* x1, const void* x1r, int H, int Wd, int OH, int OW,
+              void* out) {
+    const Plan& p = c->plan;
+    const int C = c->cfg.features;
+    const std::string n = "ref" + std::to_string(k) + ".";
+    void* tmp = buf("ref.tmp");
+    void* s = buf("ref.s");
+    void* sr = buf("ref.sr");
+    void* u = buf("ref.u");
+    void* v = buf("ref.v");
+    const void* in = x0;
+    const void* inr = x0r;
+    if (x1) {
+      rcu(n + "rcu1.", x1, x1r, x0, s, sr, p.BT, H, Wd, C, tmp);  // s = x0 + RCU1(x1)
+      in = s;
+      inr = sr;
+    }
+    rcu(n + "rcu2.", in, inr, nullptr, u, nullptr, p.BT, H, Wd, C, tmp);
+    linear(u, (long long)p.BT * H * Wd, C, n + "out.w", C, ep(v, C, wf(n + "out.b", C)));
+    upsample(L, dt, v, out, p.BT, H, Wd, OH, OW, C);
+  }
+
+  // disparity head on a feature map X [BT,H,W,F]: conv3x3 F->F/2, bilinear to (OH,OW),
+  // conv3x3 F/2->32 + ReLU, 1x1 -> 1, then ReLU (output_conv2, dpt.py:117-124) or
+  // sigmoid(sign*x) (HeadDepth, layers.py:206-217 + dpt_pyramid.py:104-109).
+  void disp_head(const std::string& c0, const std::string& c2, const std::string& c4, const void* X, int H, int Wd,
+                 int OH, int OW, float sig_sign, float* out) {
+    const Plan& p = c->plan;
+    const int F_ = c->cfg.features, Fh = F_ / 2;
+    void* o1 = buf("head.o1");
+    void* up = buf("head.up");
+    conv3(X, p.BT, H, Wd, F_, c0 + ".w", Fh, ep(o1, Fh, wf(c0 + ".b", Fh)));
+    upsample(L, dt, o1, up, p.BT, H, Wd, OH, OW, Fh);
+    const float* hw_ = wf(c4 + ".w", 33);
+    if (tc()) {
+      Epi e = ep(out, 1, wf(c2 + ".b", 32));
+      e.act = ACT_HEAD; e.head_w = hw_; e.sig_sign = sig_sign; e.out_f32 = 1;
+      e.head_b = 0.f;  // the kernel adds head_w[32]
+      conv3(up, p.BT, OH, OW, Fh, c2 + ".w", 32, e);
+    } else {
+      void* t32 = buf("head.t32");
+      Epi e = ep(t32, 32, wf(c2 + ".b", 32));
+      e.act = ACT_RELU;
+      conv3(up, p.BT, OH, OW, Fh, c2 + ".w", 32, e);
+      if (L.ok()) {
+        long long Mh = (long long)p.BT * OH * OW;
+        EDV_DISPATCH_T(dt, {
+          head_dot_kernel<T><<<nblk(Mh, 256), 256, 0, L.stream>>>((const T*)t32, hw_, out, Mh, 32, sig_sign == 0.f, sig_sign,
+                                                                sig_sign != 0.f);
+        });
+        L.check("head_dot");
+      }
+    }
+  }
+
+  int run(const void* frames, bool u8, float* const disp[4], float* resized, int out_h, int out_w) {
+    const Plan& p = c->plan;
+    const edv_config& g = c->cfg;
+    const int D = g.dim;
+    // ---- K1 + K2: preprocess, patch embedding (patch_embed.py:75-77; vision_transformer.py:219-227)
+    void* A0 = buf("A0");
+    float* x = (float*)buf("x");
+    {
+      long long tot = p.Mp * KPATCH;
+      unsigned blocks = nblk(tot, 256);
+      EDV_DISPATCH_T(dt, {
+        if (u8) preprocess_patches_kernel<T, true><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH);
+        else preprocess_patches_kernel<T, false><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH);
+      });
+      L.check("preprocess");
+      const float* cls = wf("cls_row", D);
+      if (L.ok()) {
+        cls_row_kernel<<<nblk((long long)p.BT * D, 256), 256, 0, L.stream>>>(x, cls, p.BT, p.N, D);
+        L.check("cls_row");
+      }
+      Epi e = ep(x, D, nullptr);
+      e.out_f32 = 1; e.map = MAP_TOKENS; e.map_p = p.P;
+      e.rowbias = wf("patch.pos", (size_t)p.P * D);
+      e.rb_div = 1; e.rb_mod = p.P; e.rb_ld = D;
+      linear(A0, p.Mp, KPATCH, "patch.w", D, e);
+    }
+    snapshot("tokens0", x, true, p.M, D, D);
+    // ---- encoder blocks (block.py:110-151)
+    void* xn = buf("xn");
+    void* qkv = buf("qkv");
+    void* ao = buf("ao");
+    void* hb = buf("h");
+    int tap_i = 0;
+    for (int i = 0; i < g.depth && L.ok(); ++i) {
+      const std::string n = "blk" + std::to_string(i) + ".";
+      layernorm(L, dt, x, wf(n + "ln1.w", D), wf(n + "ln1.b", D), xn, p.M, D, 1e-6f);
+      linear(xn, p.M, D, n + "qkv.w", 3 * D, ep(qkv, 3 * D, wf(n + "qkv.b", 3 * D)));
+      attention(L, dt, eng, qkv, ao, p.BT, p.N, g.heads);
+      {
+        Epi e = ep(x, D, wf(n + "proj.b", D));  // LayerScale folded into proj.w / proj.b
+        e.out_f32 = 1; e.res1 = x; e.res1_f32 = 1; e.ld_res1 = D;
+        linear(ao, p.M, D, n + "proj.w", D, e);
+      }
+      layernorm(L, dt, x, wf(n + "ln2.w", D), wf(n + "ln2.b", D), xn, p.M, D, 1e-6f);
+      {
+        Epi e = ep(hb, 4 * D, wf(n + "fc1.b", 4 * D));  // LoRA merged into fc1.w (mylora/layers.py:384-393)
+        e.act = ACT_GELU;
+        linear(xn, p.M, D, n + "fc1.w", 4 * D, e);
+      }
+      {
+        Epi e = ep(x, D, wf(n + "fc2.b", D));
+        e.out_f32 = 1; e.res1 = x; e.res1_f32 = 1; e.ld_res1 = D;
+        linear(hb, p.M, 4 * D, n + "fc2.w", D, e);
+      }
+      if (g.res_blocks & (1 << i)) res_block(n, x);
+      if (i == 0) snapshot("block0", x, true, p.M, D, D);
+      if (tap_i < 4 && i == g.taps[tap_i]) {
+        char tn[8];
+        snprintf(tn, sizeof tn, "tap%d", tap_i);
+        // final norm on the tap + cls split (vision_transformer.py:318-321)
+        layernorm(L, dt, x, wf("norm.w", D), wf("norm.b", D), buf(tn), p.Mp, D, 1e-6f, p.N, 1);
+        snapshot(tn, buf(tn), false, p.Mp, D, D);
+        ++tap_i;
+      }
+    }
+    if (tap_i != 4) L.fail(EDV_ERR_ARG, "taps must be increasing block indices < depth");
+    // ---- DPT head (dpt_pyramid.py:51-113)
+    const int F_ = g.features;
+    void* L1 = buf("L1");
+    void* L2 = buf("L2");
+    void* L3 = buf("L3");
+    void* L4p = buf("L4p");
+    void* L4 = buf("L4");
+    {
+      // projects[0] (1x1) merged with resize_layers[0] (ConvT k4 s4): one GEMM + pixel shuffle
+      Epi e = ep(L1, p.Cp[0], wf("proj0.b", 16 * p.Cp[0]));
+      e.map = MAP_PIXSHUF; e.ps_k = 4; e.ps_h = p.ph; e.ps_w = p.pw; e.ps_c = p.Cp[0];
+      linear(buf("tap0"), p.Mp, D, "proj0.w", 16 * p.Cp[0], e);
+    }
+    {
+      Epi e = ep(L2, p.Cp[1], wf("proj1.b", 4 * p.Cp[1]));
+      e.map = MAP_PIXSHUF; e.ps_k = 2; e.ps_h = p.ph; e.ps_w = p.pw; e.ps_c = p.Cp[1];
+      linear(buf("tap1"), p.Mp, D, "proj1.w", 4 * p.Cp[1], e);
+    }
+    linear(buf("tap2"), p.Mp, D, "proj2.w", p.Cp[2], ep(L3, p.Cp[2], wf("proj2.b", p.Cp[2])));
+    linear(buf("tap3"), p.Mp, D, "proj3.w", p.Cp[3], ep(L4p, p.Cp[3], wf("proj3.b", p.Cp[3])));
+    {
+      // resize_layers[3]: 3x3 stride 2 pad 1 (dpt.py:85-90) = explicit im2col + GEMM
+      const long long Mo = (long long)p.BT * p.ph2 * p.pw2;
+      if (tc()) {
+        void* col = buf("col");
+        if (L.ok()) {
+          long long tot = Mo * 9 * (p.Cp[3] / 8);
+          EDV_DISPATCH_T(dt, { im2col3x3_kernel<T><<<nblk(tot, 256), 256, 0, L.stream>>>((const T*)L4p, (T*)col, p.BT, p.ph, p.pw, p.Cp[3], p.ph2, p.pw2, 2); });
+          L.check("im2col");
+        }
+        linear(col, Mo, 9 * p.Cp[3], "resize3.w", p.Cp[3], ep(L4, p.Cp[3], wf("resize3.b", p.Cp[3])));
+      } else {
+        GemmArgs a;
+        a.A = L4p; a.W = wt("resize3.w", (size_t)p.Cp[3] * 9 * p.Cp[3]); a.M = (int)Mo; a.N = p.Cp[3]; a.K = 9 * p.Cp[3];
+        a.e = ep(L4, p.Cp[3], wf("resize3.b", p.Cp[3]));
+        a.conv = true; a.F = p.BT; a.H = p.ph; a.Wd = p.pw; a.C = p.Cp[3]; a.stride = 2;
+        if (L.ok()) gemm(L, dt, eng, a);
+      }
+    }
+    snapshot("layer1", L1, false, (long long)p.BT * 16 * p.P, p.Cp[0], g.out_channels[0]);
+    snapshot("layer2", L2, false, (long long)p.BT * 4 * p.P, p.Cp[1], g.out_channels[1]);
+    snapshot("layer3", L3, false, p.Mp, p.Cp[2], g.out_channels[2]);
+    snapshot("layer4", L4, false, (long long)p.BT * p.ph2 * p.pw2, p.Cp[3], g.out_channels[3]);
+    void* L3m = buf("L3m");
+    void* L4m = buf("L4m");
+    motion(0, L3, L3m);
+    motion(1, L4, L4m);
+    snapshot("mm0", L3m, false, p.Mp, p.Cp[2], g.out_channels[2]);
+    snapshot("mm1", L4m, false, (long long)p.BT * p.ph2 * p.pw2, p.Cp[3], g.out_channels[3]);
+    // scratch.layer{1-4}_rn (3x3, no bias) -> F channels, plus relu copies for the RCUs
+    void *l1r = buf("l1r"), *l2r = buf("l2r"), *l3r = buf("l3r"), *l4r = buf("l4r");
+    void *l1rr = buf("l1rr"), *l2rr = buf("l2rr"), *l3rr = buf("l3rr"), *l4rr = buf("l4rr");
+    {
+      Epi e = ep(l1r, F_, nullptr); e.out_relu = l1rr;
+      conv3(L1, p.BT, 4 * p.ph, 4 * p.pw, p.Cp[0], "rn1.w", F_, e);
+      e = ep(l2r, F_, nullptr); e.out_relu = l2rr;
+      conv3(L2, p.BT, 2 * p.ph, 2 * p.pw, p.Cp[1], "rn2.w", F_, e);
+      e = ep(l3r, F_, nullptr); e.out_relu = l3rr;
+      conv3(L3m, p.BT, p.ph, p.pw, p.Cp[2], "rn3.w", F_, e);
+      e = ep(l4r, F_, nullptr); e.out_relu = l4rr;
+      conv3(L4m, p.BT, p.ph2, p.pw2, p.Cp[3], "rn4.w", F_, e);
+    }
+    void *p4 = buf("p4"), *p4m = buf("p4m"), *p3 = buf("p3"), *p3m = buf("p3m"), *p2 = buf("p2"), *p1 = buf("p1");
+    fusion(4, l4r, l4rr, nullptr, nullptr, p.ph2, p.pw2, p.ph, p.pw, p4);
+    snapshot("path4_pre", p4, false, p.Mp, F_, F_);
+    motion(2, p4, p4m);
+    fusion(3, p4m, nullptr, l3r, l3rr, p.ph, p.pw, 2 * p.ph, 2 * p.pw, p3);
+    motion(3, p3, p3m);
+    snapshot("path3", p3m, false, (long long)p.BT * 4 * p.P, F_, F_);
+    fusion(2, p3m, nullptr, l2r, l2rr, 2 * p.ph, 2 * p.pw, 4 * p.ph, 4 * p.pw, p2);
+    fusion(1, p2, nullptr, l1r, l1rr, 4 * p.ph, 4 * p.pw, 8 * p.ph, 8 * p.pw, p1);
+    snapshot("path1", p1, false, (long long)p.BT * 64 * p.P, F_, F_);
+    // ---- disparity outputs
+    float* d[4];
+    for (int s = 0; s < 4; ++s) d[s] = disp[s] ? disp[s] : (float*)buf(s == 0 ? "disp0" : s == 1 ? "disp1" : s == 2 ? "disp2" : "disp3");
+    if (!g.conv_head) {
+      disp_head("oc1", "oc2a", "oc2b", p1, 8 * p.ph, 8 * p.pw, p.out_h[0], p.out_w[0], 0.f, d[0]);
+      for (int s = 1; s < 4; ++s) resize_f32(L, d[s - 1], d[s], p.BT, p.out_h[s - 1], p.out_w[s - 1], p.out_h[s], p.out_w[s]);
+      if (g.out_sigmoid && L.ok()) {
+        for (int s = 0; s < 4; ++s) {
+          long long n = (long long)p.BT * p.out_h[s] * p.out_w[s];
+          sigmoid_inplace_kernel<<<nblk(n, 256), 256, 0, L.stream>>>(d[s], n);
+          L.check("sigmoid");
+        }
+      }
+    } else {
+      const float sg = g.inv_sigmoid ? -1.f : 1.f;
+      disp_head("cd4.c0", "cd4.c2", "cd4.c4", p4m, p.ph, p.pw, p.out_h[3], p.out_w[3], sg, d[3]);
+      disp_head("cd3.c0", "cd3.c2", "cd3.c4", p3m, 2 * p.ph, 2 * p.pw, p.out_h[2], p.out_w[2], sg, d[2]);
+      disp_head("cd2.c0", "cd2.c2", "cd2.c4", p2, 4 * p.ph, 4 * p.pw, p.out_h[1], p.out_w[1], sg, d[1]);
+      disp_head("cd1.c0", "cd1.c2", "cd1.c4", p1, 8 * p.ph, 8 * p.pw, p.out_h[0], p.out_w[0], sg, d[0]);
+    }
+    if (resized) resize_f32(L, d[0], resized, p.BT, p.out_h[0], p.out_w[0], out_h, out_w);
+    c->last_launches = L.count;
+    if (!L.ok()) c->err = L.err;
+    return L.status;
+  }
+
+  // ResBottleneckBlock on the patch tokens (block.py:146-150; layers/utils.py:143-152)
+  void res_block(const std::string& n, float* x) {
+    const Plan& p = c->plan;
+    const int D = c->cfg.dim, bc = D / 8, bcp = round_up(bc, 64);
+    void* pt = buf("rb.pt");
+    void* t1 = buf("rb.t1");
+    void* t2 = buf("rb.t2");
+    void* t3 = buf("rb.t3");
+    if (!L.ok()) return;
+    EDV_DISPATCH_T(dt, {
+      tokens_to_patches_kernel<T><<<nblk(p.Mp * (D / 4), 256), 256, 0, L.stream>>>(x, (T*)pt, p.Mp, p.P, D);
+    });
+    L.check("tokens_to_patches");
+    linear(pt, p.Mp, D, n + "res.c1.w", bcp, ep(t1, bcp, nullptr));
+    if (L.ok()) {
+      EDV_DISPATCH_T(dt, { rowln_act_kernel<T><<<nblk(p.Mp * 32, 256), 256, 0, L.stream>>>((const T*)t1, wf(n + "res.n1.w", bcp), wf(n + "res.n1.b", bcp), (T*)t2, p.Mp, bcp, bc, 1e-6f, 1); });
+      L.check("res ln1");
+    }
+    conv3(t2, p.BT, p.ph, p.pw, bcp, n + "res.c2.w", bcp, ep(t1, bcp, nullptr));
+    if (L.ok()) {
+      EDV_DISPATCH_T(dt, { rowln_act_kernel<T><<<nblk(p.Mp * 32, 256), 256, 0, L.stream>>>((const T*)t1, wf(n + "res.n2.w", bcp), wf(n + "res.n2.b", bcp), (T*)t2, p.Mp, bcp, bc, 1e-6f, 1); });
+      L.check("res ln2");
+    }
+    linear(t2, p.Mp, bcp, n + "res.c3.w", D, ep(t3, D, nullptr));
+    if (L.ok()) {
+      EDV_DISPATCH_T(dt, { resblock_add_kernel<T><<<nblk(p.Mp * 32, 256), 256, 0, L.stream>>>(x, (const T*)t3, wf(n + "res.n3.w", D), wf(n + "res.n3.b", D), p.Mp, p.P, D, 1e-6f); });
+      L.check("res add");
+    }
+  }
+};
+
+int set_err(edv_ctx* c, int code, const char* fmt, ...) {
+  char b[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(b, sizeof b, fmt, ap);
+  va_end(ap);
+  if (c) c->err = b;
+  else g_create_error = b;
+  return code;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int edv_create(const edv_config* cfg, edv_ctx** out) {
+  if (!cfg || !out) return set_err(nullptr, EDV_ERR_ARG, "edv_create: null argument");
+  *out = nullptr;
+  if (cfg->dim <= 0 || cfg->dim % 64 != 0 || cfg->heads <= 0 || cfg->dim != cfg->heads * 64)
+    return set_err(nullptr, EDV_ERR_ARG, "edv_create: dim must equal heads*64 (got dim=%d heads=%d)", cfg->dim, cfg->heads);
+  if (cfg->dim > 1024) return set_err(nullptr, EDV_ERR_ARG, "edv_create: dim > 1024 unsupported");
+  if (cfg->depth <= 0 || cfg->depth > 31) return set_err(nullptr, EDV_ERR_ARG, "edv_create: bad depth %d", cfg->depth);
+  if (cfg->features % 64 != 0 || cfg->features <= 0)
+    return set_err(nullptr, EDV_ERR_ARG, "edv_create: features must be a multiple of 64");
+  if (cfg->out_channels[2] % 64 != 0 || cfg->out_channels[3] % 64 != 0)
+    return set_err(nullptr, EDV_ERR_ARG, "edv_create: out_channels[2:4] must be multiples of 64 (GroupNorm(32) inputs)");
+  if (cfg->num_frames < 1 || cfg->num_frames > 32)
+    return set_err(nullptr, EDV_ERR_ARG, "edv_create: num_frames must be in [1,32]");
+  if (cfg->dtype < EDV_F32 || cfg->dtype > EDV_F16) return set_err(nullptr, EDV_ERR_ARG, "edv_create: bad dtype");
+  if (cfg->rope) return set_err(nullptr, EDV_ERR_ARG, "edv_create: pe='rope' is not implemented yet");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(nullptr, EDV_ERR_NO_DEVICE, "edv_create: no CUDA device (this library has no CPU fallback)");
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10)
+    return set_err(nullptr, EDV_ERR_NO_DEVICE, "edv_create: device is sm_%d%d, kernels are built for sm_100a only", prop.major, prop.minor);
+  edv_ctx* c = new edv_ctx();
+  c->cfg = *cfg;
+  *out = c;
+  return EDV_OK;
+}
+
+void edv_destroy(edv_ctx* ctx) { delete ctx; }
+
+const char* edv_last_error(const edv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int edv_set_weight(edv_ctx* ctx, const char* name, const void* dev_ptr, size_t bytes) {
+  if (!ctx || !name || !dev_ptr) return set_err(ctx, EDV_ERR_ARG, "edv_set_weight: null argument");
+  if (((uintptr_t)dev_ptr & 15) != 0) return set_err(ctx, EDV_ERR_ARG, "edv_set_weight: '%s' must be 16-byte aligned", name);
+  ctx->weights[name] = WeightRef{dev_ptr, bytes};
+  return EDV_OK;
+}
+
+int edv_set_debug(edv_ctx* ctx, int on) {
+  if (!ctx) return EDV_ERR_ARG;
+  ctx->debug = on;
+  ctx->plan.valid = false;
+  return EDV_OK;
+}
+
+int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, size_t* workspace_bytes) {
+  if (!ctx || !workspace_bytes) return set_err(ctx, EDV_ERR_ARG, "edv_plan: null argument");
+  const edv_config& g = ctx->cfg;
+  if (B < 1 || T < 1 || T > g.num_frames)
+    return set_err(ctx, EDV_ERR_ARG, "edv_plan: T=%d must be in [1,num_frames=%d] (PE table, motion_module.py:185-197)", T, g.num_frames);
+  if (net_h % 14 != 0 || net_w % 14 != 0 || net_h < 14 || net_w < 14)
+    return set_err(ctx, EDV_ERR_ARG, "edv_plan: network resolution %dx%d must be multiples of 14 (patch_embed.py:72-73)", net_h, net_w);
+  if (H < 1 || W < 1) return set_err(ctx, EDV_ERR_ARG, "edv_plan: bad frame size");
+  Plan p;
+  p.B = B; p.T = T; p.H = H; p.W = W; p.h = net_h; p.w = net_w;
+  p.BT = B * T; p.ph = net_h / 14; p.pw = net_w / 14; p.P = p.ph * p.pw; p.N = p.P + 1;
+  p.M = (long long)p.BT * p.N; p.Mp = (long long)p.BT * p.P;
+  p.ph2 = (p.ph - 1) / 2 + 1; p.pw2 = (p.pw - 1) / 2 + 1;
+  if (p.M * 4LL * g.dim > 2000000000LL * 4) return set_err(ctx, EDV_ERR_ARG, "edv_plan: clip batch too large for 32-bit row indexing");
+  for (int i = 0; i < 4; ++i) p.Cp[i] = round_up(g.out_channels[i], 64);
+  if (g.res_blocks) {
+    if (g.dim % 8 != 0) return set_err(ctx, EDV_ERR_ARG, "edv_plan: residual blocks need dim %% 8 == 0");
+  }
+  const int F_ = g.features, Fh = F_ / 2;
+  p.mm[0] = MMPlan{p.Cp[2], p.ph, p.pw};
+  p.mm[1] = MMPlan{p.Cp[3], p.ph2, p.pw2};
+  p.mm[2] = MMPlan{F_, p.ph, p.pw};
+  p.mm[3] = MMPlan{F_, 2 * p.ph, 2 * p.pw};
+  for (int j = 0; j < 4; ++j) {
+    int hd = p.mm[j].C / 8;
+    if (!(hd == 8 || hd == 24 || hd == 32 || hd == 48 || hd == 128))
+      return set_err(ctx, EDV_ERR_ARG, "edv_plan: temporal head dim %d unsupported (8,24,32,48,128)", hd);
+  }
+  if (!g.conv_head) {
+    p.out_h[0] = net_h; p.out_w[0] = net_w;
+    for (int s = 1; s < 4; ++s) { p.out_h[s] = p.out_h[s - 1] / 2; p.out_w[s] = p.out_w[s - 1] / 2; }  // scale_factor=0.5 -> floor
+  } else {
+    p.out_h[0] = 16 * p.ph; p.out_w[0] = 16 * p.pw;   // HeadDepth upsamples x2 (layers.py:211)
+    p.out_h[1] = 8 * p.ph; p.out_w[1] = 8 * p.pw;
+    p.out_h[2] = 4 * p.ph; p.out_w[2] = 4 * p.pw;
+    p.out_h[3] = 2 * p.ph; p.out_w[3] = 2 * p.pw;
+  }
+  for (int s = 0; s < 4; ++s)
+    if (p.out_h[s] < 1 || p.out_w[s] < 1) return set_err(ctx, EDV_ERR_ARG, "edv_plan: resolution too small for the 4-level pyramid");
+
+  const size_t es = dtype_size(g.dtype);
+  size_t off = 0;
+  auto add = [&](const char* name, size_t bytes) {
+    Buf b;
+    b.off = off;
+    b.bytes = bytes;
+    p.bufs[name] = b;
+    off += (bytes + 1023) & ~(size_t)1023;
+  };
+  const int D = g.dim;
+  add("A0", (size_t)p.Mp * KPATCH * es);
+  add("x", (size_t)p.M * D * 4);
+  add("xn", (size_t)p.M * D * es);
+  add("qkv", (size_t)p.M * 3 * D * es);
+  add("ao", (size_t)p.M * D * es);
+  add("h", (size_t)p.M * 4 * D * es);
+  for (int i = 0; i < 4; ++i) {
+    char n[8];
+    snprintf(n, sizeof n, "tap%d", i);
+    add(n, (size_t)p.Mp * D * es);
+  }
+  if (g.res_blocks) {
+    const int bcp = round_up(D / 8, 64);
+    add("rb.pt", (size_t)p.Mp * D * es);
+    add("rb.t1", (size_t)p.Mp * bcp * es);
+    add("rb.t2", (size_t)p.Mp * bcp * es);
+    add("rb.t3", (size_t)p.Mp * D * es);
+  }
+  const size_t px1 = (size_t)p.BT * 16 * p.P, px2 = (size_t)p.BT * 4 * p.P, px3 = (size_t)p.Mp, px4 = (size_t)p.BT * p.ph2 * p.pw2;
+  const size_t px0 = (size_t)p.BT * 64 * p.P;  // 8ph x 8pw
+  add("L1", px1 * p.Cp[0] * es);
+  add("L2", px2 * p.Cp[1] * es);
+  add("L3", px3 * p.Cp[2] * es);
+  add("L4p", px3 * p.Cp[3] * es);
+  add("L4", px4 * p.Cp[3] * es);
+  add("col", px4 * 9 * p.Cp[3] * es);
+  add("L3m", px3 * p.Cp[2] * es);
+  add("L4m", px4 * p.Cp[3] * es);
+  // motion-module scratch, sized for the largest of the four modules
+  size_t mmC = 0, mm3 = 0, mm4 = 0, mm8 = 0;
+  for (int j = 0; j < 4; ++j) {
+    size_t rows = (size_t)p.BT * p.mm[j].h * p.mm[j].w, C = p.mm[j].C;
+    mmC = std::max(mmC, rows * C);
+    mm3 = std::max(mm3, rows * 3 * C);
+    mm4 = std::max(mm4, rows * 4 * C);
+    mm8 = std::max(mm8, rows * 8 * C);
+  }
+  add("mm.stats", (size_t)p.BT * 32 * sizeof(float2));
+  add("mm.gn", mmC * es);
+  add("mm.hs", mmC * 4);
+  add("mm.ln", mmC * es);
+  add("mm.qkv", mm3 * es);
+  add("mm.att", mmC * es);
+  add("mm.gg", mm4 * es);
+  add("mm.hsT", mmC * es);
+  const bool simt = (g.dtype == EDV_F32) || g.engine == EDV_ENGINE_SIMT;
+  if (simt) add("mm.gg2", mm8 * es);
+  add("l1r", px1 * F_ * es); add("l1rr", px1 * F_ * es);
+  add("l2r", px2 * F_ * es); add("l2rr", px2 * F_ * es);
+  add("l3r", px3 * F_ * es); add("l3rr", px3 * F_ * es);
+  add("l4r", px4 * F_ * es); add("l4rr", px4 * F_ * es);
+  // refinenet scratch at the largest input resolution (refinenet1 runs at 4ph x 4pw)
+  add("ref.tmp", px1 * F_ * es);
+  add("ref.s", px1 * F_ * es);
+  add("ref.sr", px1 * F_ * es);
+  add("ref.u", px1 * F_ * es);
+  add("ref.v", px1 * F_ * es);
+  add("p4", px3 * F_ * es); add("p4m", px3 * F_ * es);
+  add("p3", px2 * F_ * es); add("p3m", px2 * F_ * es);
+  add("p2", px1 * F_ * es);
+  add("p1", px0 * F_ * es);
+  // disparity head scratch: conv at up to 8ph x 8pw, upsample target up to out_h[0] x out_w[0]
+  const size_t pxo = (size_t)p.BT * p.out_h[0] * p.out_w[0];
+  add("head.o1", px0 * Fh * es);
+  add("head.up", pxo * Fh * es);
+  if (simt) add("head.t32", pxo * 32 * es);
+  for (int s = 0; s < 4; ++s) {
+    char n[8];
+    snprintf(n, sizeof n, "disp%d", s);
+    add(n, (size_t)p.BT * p.out_h[s] * p.out_w[s] * 4);
+  }
+  if (ctx->debug) {
+    auto tap = [&](const char* name, long long rows, int cols) {
+      DebugTap t;
+      t.rows = rows;
+      t.cols = cols;
+      t.buf.off = off;
+      t.buf.bytes = (size_t)rows * cols * 4;
+      off += (t.buf.bytes + 1023) & ~(size_t)1023;
+      p.taps[name] = t;
+    };
+    tap("tokens0", p.M, D);
+    tap("block0", p.M, D);
+    for (int i = 0; i < 4; ++i) {
+      char n[8];
+      snprintf(n, sizeof n, "tap%d", i);
+      tap(n, p.Mp, D);
+    }
+    tap("layer1", px1, g.out_channels[0]);
+    tap("layer2", px2, g.out_channels[1]);
+    tap("layer3", px3, g.out_channels[2]);
+    tap("layer4", px4, g.out_channels[3]);
+    tap("mm0", px3, g.out_channels[2]);
+    tap("mm1", px4, g.out_channels[3]);
+    tap("path4_pre", px3, F_);
+    tap("path3", px2, F_);
+    tap("path1", px0, F_);
+  }
+  p.total = off + 1024;
+  p.valid = true;
+  ctx->plan = p;
+  *workspace_bytes = p.total;
+  return EDV_OK;
+}
+
+static int forward_common(edv_ctx* ctx, const void* frames, bool u8, float* const disp_dev[4], float* resized_dev,
+                          int out_h, int out_w, void* workspace_dev, void* stream) {
+  if (!ctx || !frames || !workspace_dev) return set_err(ctx, EDV_ERR_ARG, "edv_forward: null argument");
+  if (!ctx->plan.valid) return set_err(ctx, EDV_ERR_STATE, "edv_forward: call edv_plan first");
+  if (((uintptr_t)workspace_dev & 1023) != 0) return set_err(ctx, EDV_ERR_ARG, "edv_forward: workspace must be 1024-byte aligned");
+  if (resized_dev && (out_h < 1 || out_w < 1)) return set_err(ctx, EDV_ERR_ARG, "edv_forward: bad resize target");
+  if (u8 && (ctx->plan.H != ctx->plan.h || ctx->plan.W != ctx->plan.w))
+    return set_err(ctx, EDV_ERR_ARG, "edv_forward_u8: frames must already be at network resolution");
+  float* none[4] = {nullptr, nullptr, nullptr, nullptr};
+  Fwd f(ctx, workspace_dev, (cudaStream_t)stream);
+  return f.run(frames, u8, disp_dev ? disp_dev : none, resized_dev, out_h, out_w);
+}
+
+int edv_forward(edv_ctx* ctx, const float* frames_dev, float* const disp_dev[4], float* resized_dev, int out_h,
+                int out_w, void* workspace_dev, void* stream) {
+  return forward_common(ctx, frames_dev, false, disp_dev, resized_dev, out_h, out_w, workspace_dev, stream);
+}
+
+int edv_forward_u8(edv_ctx* ctx, const uint8_t* frames_dev, float* const disp_dev[4], float* resized_dev, int out_h,
+                   int out_w, void* workspace_dev, void* stream) {
+  return forward_common(ctx, frames_dev, true, disp_dev, resized_dev, out_h, out_w, workspace_dev, stream);
+}
+
+int edv_output_shape(const edv_ctx* ctx, int scale, int* h, int* w) {
+  if (!ctx || !ctx->plan.valid || scale < 0 || scale > 3 || !h || !w) return EDV_ERR_ARG;
+  *h = ctx->plan.out_h[scale];
+  *w = ctx->plan.out_w[scale];
+  return EDV_OK;
+}
+
+int edv_launch_count(const edv_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+// workspace offset of a debug tap (the Python host slices its own workspace tensor)
+int edv_debug_tap(edv_ctx* ctx, const char* name, size_t* offset_bytes, long long* rows, int* cols) {
+  if (!ctx || !name || !offset_bytes || !rows || !cols) return EDV_ERR_ARG;
+  if (!ctx->debug || !ctx->plan.valid) return set_err(ctx, EDV_ERR_STATE, "edv_debug_tap: enable edv_set_debug before edv_plan");
+  auto it = ctx->plan.taps.find(name);
+  if (it == ctx->plan.taps.end()) return set_err(ctx, EDV_ERR_ARG, "edv_debug_tap: unknown tap '%s'", name);
+  *offset_bytes = it->second.buf.off;
+  *rows = it->second.rows;
+  *cols = it->second.cols;
+  return EDV_OK;
+}
+
+// ---- per-kernel entry points ----------------------------------------------------------------
+static int finish(Launch& L) {
+  if (!L.ok()) g_create_error = L.err;
+  return L.status;
+}
+
+int edv_op_linear(int dtype, int engine, const void* A, const void* W, const float* bias, void* C, int M, int N, int K,
+                  int act, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  GemmArgs a;
+  a.A = A; a.W = W; a.M = M; a.N = N; a.K = K; a.lda = K;
+  a.e = epi_zero();
+  a.e.out = C; a.e.ldo = N; a.e.bias = bias; a.e.act = act;
+  if (act != ACT_NONE && act != ACT_GELU && act != ACT_RELU) return EDV_ERR_ARG;
+  gemm(L, dtype, engine, a);
+  return finish(L);
+}
+
+int edv_op_conv3x3(int dtype, int engine, const void* X, const void* Wt, const float* bias, void* Y, int F, int H,
+                   int W, int Cin, int Cout, int relu_out, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  GemmArgs a;
+  a.A = X; a.W = Wt; a.M = F * H * W; a.N = Cout; a.K = 9 * Cin;
+  a.e = epi_zero();
+  a.e.out = Y; a.e.ldo = Cout; a.e.bias = bias; a.e.act = relu_out ? ACT_RELU : ACT_NONE;
+  a.conv = true; a.F = F; a.H = H; a.Wd = W; a.C = Cin; a.stride = 1;
+  gemm(L, dtype, engine, a);
+  return finish(L);
+}
+
+int edv_op_attention(int dtype, int engine, const void* qkv, void* out, int F, int S, int heads, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  attention(L, dtype, engine, qkv, out, F, S, heads);
+  return finish(L);
+}
+
+int edv_op_temporal_attention(int dtype, const void* qkv, void* out, int B, int T, int hw, int C, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  temporal_attention(L, dtype, qkv, out, B, T, hw, C);
+  return finish(L);
+}
+
+int edv_op_layernorm(int dtype, const float* X, const float* gamma, const float* beta, void* Y, int M, int D,
+                     float eps, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  layernorm(L, dtype, X, gamma, beta, Y, M, D, eps);
+  return finish(L);
+}
+
+int edv_op_groupnorm(int dtype, const void* X, const float* gamma, const float* beta, void* Y, int F, int hw, int C,
+                     float eps, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  float2* stats = nullptr;
+  if (cudaMallocAsync((void**)&stats, (size_t)F * 32 * sizeof(float2), L.stream) != cudaSuccess) return EDV_ERR_CUDA;
+  groupnorm(L, dtype, X, gamma, beta, Y, stats, F, hw, C, eps);
+  cudaFreeAsync(stats, L.stream);
+  return finish(L);
+}
+
+int edv_op_upsample(int dtype, const void* X, void* Y, int F, int h, int w, int oh, int ow, int C, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  upsample(L, dtype, X, Y, F, h, w, oh, ow, C);
+  return finish(L);
+}
+
+int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int ow, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  resize_f32(L, X, Y, F, h, w, oh, ow);
+  return finish(L);
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+// Host-side launchers shared by the forward graph (engine.cu) and the per-kernel C entry
+// points.  Everything is stream-ordered; no allocation, no synchronisation.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/endodav_b200.h"
+#include "launch.h"
+#include "attention_simt.cuh"
+#include "attention_tc.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace edv {
+
+inline size_t dtype_size(int dtype) { return dtype == EDV_F32 ? 4 : 2; }
+
+// ---- TMA descriptor encoding (driver entry point fetched through the runtime, so the
+// library carries no link-time dependency on libcuda) --------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// rank-R tiled map over a 16-bit tensor; dims/box innermost first; strides in bytes for dims 1..R-1
+inline bool make_tmap(Launch& L, CUtensorMap* m, int dtype, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (!fn) {
+    L.fail(EDV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    return false;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMapDataType dt = dtype == EDV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu box %u,%u", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    L.fail(EDV_ERR_CUDA, buf);
+    return false;
+  }
+  return true;
+}
+
+// ---- GEMM -----------------------------------------------------------------------------------
+struct GemmArgs {
+  const void* A = nullptr;   // [M,K] (lda) or NHWC activation for conv
+  const void* W = nullptr;   // [N,K]
+  int M = 0, N = 0, K = 0;
+  long long lda = 0;
+  Epi e{};
+  // conv (3x3, pad 1)
+  bool conv = false;
+  int F = 0, H = 0, Wd = 0, C = 0, stride = 1;
+};
+
+inline Epi epi_zero() {
+  Epi e;
+  memset(&e, 0, sizeof e);
+  e.rb_div = 1;
+  e.rb_mod = 1;
+  return e;
+}
+
+template <typename T> void launch_gemm_simt(Launch& L, const GemmArgs& a) {
+  dim3 grid((a.N + SG_BN - 1) / SG_BN, (unsigned)((a.M + SG_BM - 1) / SG_BM));
+  ConvGeom g{};
+  if (a.conv) {
+    g.H = a.H; g.W = a.Wd; g.C = a.C; g.stride = a.stride;
+    g.OH = (a.H - 1) / a.stride + 1;
+    g.OW = (a.Wd - 1) / a.stride + 1;
+    gemm_simt_kernel<T, true><<<grid, 256, 0, L.stream>>>((const T*)a.A, (const T*)a.W, a.e, a.M, a.N, a.K, a.lda, g);
+  } else {
+    gemm_simt_kernel<T, false><<<grid, 256, 0, L.stream>>>((const T*)a.A, (const T*)a.W, a.e, a.M, a.N, a.K, a.lda, g);
+  }
+  L.check("gemm_simt");
+}
+
+// choose the conv tile shape (th*tw == 128) wasting the fewest pixels
+inline void pick_conv_tile(int H, int W, int* th, int* tw) {
+  const int cand[6][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {1, 128}};
+  long long best = -1;
+  for (auto& c : cand) {
+    long long cover = (long long)((H + c[0] - 1) / c[0]) * c[0] * ((W + c[1] - 1) / c[1]) * c[1];
+    if (best < 0 || cover < best) {
+      best = cover;
+      *th = c[0];
+      *tw = c[1];
+    }
+  }
+}
+
+template <typename T, int BN, int BK, bool CONV>
+void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
+  using namespace tc;
+  CUtensorMap tmA, tmB;
+  ConvTile ct{};
+  long long m_tiles;
+  const int swz = BK * 2;
+  if (CONV) {
+    ct.H = a.H; ct.W = a.Wd; ct.C = a.C;
+    pick_conv_tile(a.H, a.Wd, &ct.th, &ct.tw);
+    ct.tiles_y = (a.H + ct.th - 1) / ct.th;
+    ct.tiles_x = (a.Wd + ct.tw - 1) / ct.tw;
+    m_tiles = (long long)a.F * ct.tiles_y * ct.tiles_x;
+    uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.Wd, (uint64_t)a.H, (uint64_t)a.F};
+    uint64_t str[3] = {(uint64_t)a.C * 2, (uint64_t)a.C * a.Wd * 2, (uint64_t)a.C * a.Wd * a.H * 2};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)ct.tw, (uint32_t)ct.th, 1};
+    if (!make_tmap(L, &tmA, dtype, a.A, 4, dims, str, box, swz)) return;
+  } else {
+    m_tiles = (a.M + GT_BM - 1) / GT_BM;
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.lda * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmA, dtype, a.A, 2, dims, str, box, swz)) return;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t str[1] = {(uint64_t)a.K * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    if (!make_tmap(L, &tmB, dtype, a.W, 2, dims, str, box, swz)) return;
+  }
+  const int kblocks = a.K / BK;
+  const int stage_bytes = gt_stage_bytes<BN, BK>();
+  int stages = (96 * 1024) / stage_bytes;  // two CTAs per SM
+  if (stages > kblocks) stages = kblocks;
+  if (stages < 2) stages = kblocks < 2 ? 1 : 2;
+  if (stages > 8) stages = 8;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16;
+  auto kern = gemm_tc_kernel<T, BN, BK, CONV>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const long long blocks = m_tiles * (a.N / BN);
+  kern<<<(unsigned)blocks, GT_THREADS, smem, L.stream>>>(tmA, tmB, a.e, a.M, a.N, a.K, stages, ct);
+  L.check("gemm_tc");
+}
+
+template <typename T> void launch_gemm_tc(Launch& L, int dtype, const GemmArgs& a) {
+  const bool small_k = a.conv ? (a.C % 64 != 0) : (a.K % 64 != 0);
+  const int bk = small_k ? 32 : 64;
+  if ((a.conv ? a.C : a.K) % bk != 0) return L.fail(EDV_ERR_ARG, "gemm_tc: K (or conv C) must be a multiple of 32");
+  if (a.conv && a.stride != 1) return L.fail(EDV_ERR_ARG, "gemm_tc: conv stride must be 1");
+  int bn;
+  if (a.e.act == ACT_GEGLU) bn = 128;
+  else if (a.e.act == ACT_HEAD) bn = 32;
+  else bn = (a.N % 128 == 0) ? 128 : (a.N % 64 == 0) ? 64 : 32;
+  if (a.N % bn != 0) return L.fail(EDV_ERR_ARG, "gemm_tc: N must be a multiple of 32");
+  if (a.e.act == ACT_HEAD && a.N != 32) return L.fail(EDV_ERR_ARG, "gemm_tc: head epilogue needs N == 32");
+#define EDV_TC_CASE(BN_, BK_)                                                         \
+  if (bn == BN_ && bk == BK_) {                                                       \
+    if (a.conv) launch_gemm_tc_inst<T, BN_, BK_, true>(L, dtype, a);                  \
+    else launch_gemm_tc_inst<T, BN_, BK_, false>(L, dtype, a);                        \
+    return;                                                                           \
+  }
+  EDV_TC_CASE(128, 64)
+  EDV_TC_CASE(64, 64)
+  EDV_TC_CASE(32, 64)
+  EDV_TC_CASE(128, 32)
+  EDV_TC_CASE(64, 32)
+  EDV_TC_CASE(32, 32)
+#undef EDV_TC_CASE
+  L.fail(EDV_ERR_ARG, "gemm_tc: no instantiation");
+}
+
+// dispatch on dtype / engine.  GEGLU and HEAD epilogues exist only in the tcgen05 kernel;
+// the CUDA-core path composes them from a plain GEMM plus a small kernel (see engine.cu).
+inline void gemm(Launch& L, int dtype, int engine, const GemmArgs& a) {
+  if (!L.ok()) return;
+  if (dtype == EDV_F32) return launch_gemm_simt<float>(L, a);
+  if (engine == EDV_ENGINE_SIMT) {
+    if (dtype == EDV_BF16) return launch_gemm_simt<bf16>(L, a);
+    return launch_gemm_simt<f16>(L, a);
+  }
+  if (dtype == EDV_BF16) return launch_gemm_tc<bf16>(L, dtype, a);
+  return launch_gemm_tc<f16>(L, dtype, a);
+}
+
+// ---- elementwise launchers --------------------------------------------------------------------
+#define EDV_DISPATCH_T(dtype, ...)                      \
+  do {                                                  \
+    if ((dtype) == EDV_F32) { using T = float; __VA_ARGS__; } \
+    else if ((dtype) == EDV_BF16) { using T = bf16; __VA_ARGS__; } \
+    else { using T = f16; __VA_ARGS__; }                \
+  } while (0)
+
+inline unsigned nblk(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+inline void layernorm(Launch& L, int dtype, const float* x, const float* g, const float* b, void* y, long long Mout,
+                      int D, float eps, int grp = 0, int skip = 0) {
+  if (!L.ok()) return;
+  if (D % 4 != 0 || D > 1024) return L.fail(EDV_ERR_ARG, "layernorm: D must be a multiple of 4 and <= 1024");
+  const int maxv = (D + 127) / 128;
+  const unsigned blocks = nblk(Mout * 32, 256);
+  EDV_DISPATCH_T(dtype, {
+    if (maxv <= 1) layernorm_kernel<T, 1><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
+    else if (maxv <= 2) layernorm_kernel<T, 2><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
+    else if (maxv <= 3) layernorm_kernel<T, 3><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
+    else if (maxv <= 4) layernorm_kernel<T, 4><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
+    else layernorm_kernel<T, 8><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
+  });
+  L.check("layernorm");
+}
+
+inline void groupnorm(Launch& L, int dtype, const void* x, const float* g, const float* b, void* y, float2* stats,
+                      int F, int hw, int C, float eps) {
+  if (!L.ok()) return;
+  if (C % 32 != 0 || C % 8 != 0) return L.fail(EDV_ERR_ARG, "groupnorm: C must be a multiple of 32");
+  EDV_DISPATCH_T(dtype, {
+    groupnorm_stats_kernel<T><<<dim3(32, F), 256, 0, L.stream>>>((const T*)x, stats, hw, C, eps);
+    L.check("groupnorm_stats");
+    long long total8 = (long long)F * hw * C / 8;
+    groupnorm_apply_kernel<T><<<nblk(total8, 256), 256, 0, L.stream>>>((const T*)x, stats, g, b, (T*)y, total8, hw, C);
+  });
+  L.check("groupnorm_apply");
+}
+
+inline void upsample(Launch& L, int dtype, const void* x, void* y, int F, int h, int w, int oh, int ow, int C) {
+  if (!L.ok()) return;
+  if (C % 8 != 0) return L.fail(EDV_ERR_ARG, "upsample: C must be a multiple of 8");
+  long long total = (long long)F * oh * ow * (C / 8);
+  EDV_DISPATCH_T(dtype, { upsample_nhwc_kernel<T><<<nblk(total, 256), 256, 0, L.stream>>>((const T*)x, (T*)y, F, h, w, oh, ow, C); });
+  L.check("upsample");
+}
+
+inline void resize_f32(Launch& L, const float* x, float* y, int F, int h, int w, int oh, int ow, int sigmoid = 0) {
+  if (!L.ok()) return;
+  long long total = (long long)F * oh * ow;
+  resize_f32_kernel<<<nblk(total, 256), 256, 0, L.stream>>>(x, y, F, h, w, oh, ow, sigmoid);
+  L.check("resize_f32");
+}
+
+inline void attention(Launch& L, int dtype, int engine, const void* qkv, void* out, int F, int S, int heads) {
+  if (!L.ok()) return;
+  if (dtype != EDV_F32 && engine == EDV_ENGINE_TC) {
+    if (dtype == EDV_BF16) tc::launch_attention_tc<bf16>(L, dtype, qkv, out, F, S, heads);
+    else tc::launch_attention_tc<f16>(L, dtype, qkv, out, F, S, heads);
+    return;
+  }
+  dim3 grid((S + 127) / 128, heads, F);
+  EDV_DISPATCH_T(dtype, { spatial_attention_simt_kernel<T><<<grid, 128, 0, L.stream>>>((const T*)qkv, (T*)out, S, heads); });
+  L.check("spatial_attention_simt");
+}
+
+template <typename T, int HD>
+void launch_temporal(Launch& L, const void* qkv, void* out, int B, int Tn, int hw, int C) {
+  const int heads = 8;
+  int hpb = heads;
+  auto smem_for = [&](int h) { return (size_t)Tn * (3 * h * HD + 1) * sizeof(float); };
+  while (hpb > 1 && smem_for(hpb) > 100 * 1024) hpb >>= 1;
+  const size_t smem = smem_for(hpb);
+  auto kern = temporal_attention_kernel<T, HD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  dim3 grid(hw, B, heads / hpb);
+  kern<<<grid, 32 * hpb, smem, L.stream>>>((const T*)qkv, (T*)out, Tn, hw, C, hpb);
+  L.check("temporal_attention");
+}
+
+inline void temporal_attention(Launch& L, int dtype, const void* qkv, void* out, int B, int Tn, int hw, int C) {
+  if (!L.ok()) return;
+  if (Tn > 32 || Tn < 1) return L.fail(EDV_ERR_ARG, "temporal attention: T must be in [1,32] (motion_module.py:185-197)");
+  if (C % 8 != 0) return L.fail(EDV_ERR_ARG, "temporal attention: C must be a multiple of 8");
+  const int hd = C / 8;
+#define EDV_TA_CASE(HD_)                                                                   \
+  if (hd == HD_) {                                                                         \
+    EDV_DISPATCH_T(dtype, { launch_temporal<T, HD_>(L, qkv, out, B, Tn, hw, C); });        \
+    return;                                                                                \
+  }
+  EDV_TA_CASE(8)
+  EDV_TA_CASE(24)
+  EDV_TA_CASE(32)
+  EDV_TA_CASE(48)
+  EDV_TA_CASE(128)
+#undef EDV_TA_CASE
+  L.fail(EDV_ERR_ARG, "temporal attention: unsupported head dim (supported 8,24,32,48,128)");
+}
+
+}  // namespace edv

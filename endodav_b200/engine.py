@@ -1,0 +1,259 @@
+"""ctypes binding of the C-ABI library (include/endodav_b200.h).
+
+There is deliberately no fallback: if ``libendodav_b200.so`` is missing or no sm_100 GPU is
+present, every entry point raises.  torch is used only for device memory and streams."""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libendodav_b200.so")
+
+EDV_F32, EDV_BF16, EDV_F16 = 0, 1, 2
+ENGINE_TC, ENGINE_SIMT = 0, 1
+DTYPES = {"fp32": EDV_F32, "f32": EDV_F32, "float32": EDV_F32, "bf16": EDV_BF16, "bfloat16": EDV_BF16,
+          "fp16": EDV_F16, "f16": EDV_F16, "float16": EDV_F16}
+TORCH_DTYPE = {EDV_F32: torch.float32, EDV_BF16: torch.bfloat16, EDV_F16: torch.float16}
+
+EXPORTS = [
+    "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
+    "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_op_linear", "edv_op_conv3x3",
+    "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
+    "edv_op_resize_f32",
+]
+
+
+class EdvConfig(ctypes.Structure):
+    _fields_ = [
+        ("dim", ctypes.c_int32), ("depth", ctypes.c_int32), ("heads", ctypes.c_int32), ("taps", ctypes.c_int32 * 4),
+        ("features", ctypes.c_int32), ("out_channels", ctypes.c_int32 * 4), ("num_frames", ctypes.c_int32),
+        ("conv_head", ctypes.c_int32), ("out_sigmoid", ctypes.c_int32), ("inv_sigmoid", ctypes.c_int32),
+        ("res_blocks", ctypes.c_int32), ("rope", ctypes.c_int32), ("dtype", ctypes.c_int32), ("engine", ctypes.c_int32),
+    ]
+
+
+class EndoDAVError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EndoDAVError(
+            "endodav_b200: %s is missing -- build it with `python -m endodav_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.edv_create.argtypes = [ctypes.POINTER(EdvConfig), ctypes.POINTER(vp)]
+    lib.edv_destroy.argtypes = [vp]
+    lib.edv_destroy.restype = None
+    lib.edv_last_error.argtypes = [vp]
+    lib.edv_last_error.restype = ctypes.c_char_p
+    lib.edv_set_weight.argtypes = [vp, ctypes.c_char_p, vp, sz]
+    lib.edv_plan.argtypes = [vp, ci, ci, ci, ci, ci, ci, ctypes.POINTER(sz)]
+    lib.edv_forward.argtypes = [vp, vp, ctypes.POINTER(vp), vp, ci, ci, vp, vp]
+    lib.edv_forward_u8.argtypes = [vp, vp, ctypes.POINTER(vp), vp, ci, ci, vp, vp]
+    lib.edv_output_shape.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.edv_launch_count.argtypes = [vp]
+    lib.edv_set_debug.argtypes = [vp, ci]
+    lib.edv_debug_tap.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_longlong),
+                                  ctypes.POINTER(ci)]
+    lib.edv_op_linear.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.edv_op_conv3x3.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.edv_op_attention.argtypes = [ci, ci, vp, vp, ci, ci, ci, vp]
+    lib.edv_op_temporal_attention.argtypes = [ci, vp, vp, ci, ci, ci, ci, vp]
+    lib.edv_op_layernorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ctypes.c_float, vp]
+    lib.edv_op_groupnorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
+    lib.edv_op_upsample.argtypes = [ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.edv_op_resize_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("edv_destroy", "edv_last_error"):
+            fn.restype = ci
+    _lib = lib
+    return lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _check(rc, ctx=None, what=""):
+    if rc != 0:
+        lib = load_library()
+        msg = lib.edv_last_error(ctx if ctx is not None else ctypes.c_void_p(0))
+        raise EndoDAVError("%s failed (%d): %s" % (what, rc, (msg or b"").decode("utf-8", "replace")))
+
+
+class Engine:
+    """One ``edv_ctx``: a model on one device.  Holds the packed weights (so the borrowed device
+    pointers stay alive) and one workspace per planned shape."""
+
+    def __init__(self, cfg: EdvConfig, device):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise EndoDAVError("endodav_b200 runs on CUDA devices only (got %s)" % (device,))
+        self.cfg = cfg
+        self.ctx = ctypes.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _check(self.lib.edv_create(ctypes.byref(cfg), ctypes.byref(self.ctx)), None, "edv_create")
+        self.weights = {}
+        self.shape_key = None
+        self.workspace = None
+        self.debug = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None) and self.ctx.value:
+                self.lib.edv_destroy(self.ctx)
+                self.ctx = ctypes.c_void_p(0)
+        except Exception:
+            pass
+
+    def set_weights(self, packed: dict):
+        for name, t in packed.items():
+            t = t.to(self.device).contiguous()
+            self.weights[name] = t
+            _check(self.lib.edv_set_weight(self.ctx, name.encode(), _ptr(t), t.numel() * t.element_size()), self.ctx,
+                   "edv_set_weight(%s)" % name)
+
+    def set_debug(self, on: bool):
+        self.debug = bool(on)
+        _check(self.lib.edv_set_debug(self.ctx, int(on)), self.ctx, "edv_set_debug")
+        self.shape_key = None
+
+    def plan(self, B, T, H, W, net_h, net_w):
+        key = (B, T, H, W, net_h, net_w)
+        if key == self.shape_key:
+            return False
+        nbytes = ctypes.c_size_t(0)
+        _check(self.lib.edv_plan(self.ctx, B, T, H, W, net_h, net_w, ctypes.byref(nbytes)), self.ctx, "edv_plan")
+        if self.workspace is None or self.workspace.numel() < nbytes.value + 1024:
+            self.workspace = None
+            self.workspace = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
+        self.shape_key = key
+        return True
+
+    def _ws_ptr(self):
+        base = self.workspace.data_ptr()
+        return (base + 1023) & ~1023
+
+    def output_shapes(self):
+        out = []
+        for s in range(4):
+            h, w = ctypes.c_int(0), ctypes.c_int(0)
+            _check(self.lib.edv_output_shape(self.ctx, s, ctypes.byref(h), ctypes.byref(w)), self.ctx, "edv_output_shape")
+            out.append((h.value, w.value))
+        return out
+
+    def forward(self, frames, resize_to=None, want_pyramid=True):
+        """frames: float32 [B,T,3,H,W] (or uint8 [B*T,H,W,3] at network resolution) on this
+        device.  Returns (list of 4 disparity tensors [BT,1,h_s,w_s] or None, resized or None)."""
+        BT = self.shape_key[0] * self.shape_key[1]
+        shapes = self.output_shapes()
+        disp = [torch.empty(BT, 1, h, w, dtype=torch.float32, device=self.device) for (h, w) in shapes] if want_pyramid else None
+        arr = (ctypes.c_void_p * 4)(*([_ptr(d) for d in disp] if disp else [None] * 4))
+        resized = None
+        oh = ow = 0
+        if resize_to is not None:
+            oh, ow = resize_to
+            resized = torch.empty(BT, oh, ow, dtype=torch.float32, device=self.device)
+        fn = self.lib.edv_forward_u8 if frames.dtype == torch.uint8 else self.lib.edv_forward
+        rc = fn(self.ctx, _ptr(frames), arr, _ptr(resized), oh, ow, ctypes.c_void_p(self._ws_ptr()), _stream())
+        _check(rc, self.ctx, "edv_forward")
+        return disp, resized
+
+    def launch_count(self):
+        return int(self.lib.edv_launch_count(self.ctx))
+
+    def debug_tap(self, name):
+        off, rows, cols = ctypes.c_size_t(0), ctypes.c_longlong(0), ctypes.c_int(0)
+        _check(self.lib.edv_debug_tap(self.ctx, name.encode(), ctypes.byref(off), ctypes.byref(rows), ctypes.byref(cols)),
+               self.ctx, "edv_debug_tap")
+        start = self._ws_ptr() - self.workspace.data_ptr() + off.value
+        n = rows.value * cols.value
+        return self.workspace[start:start + 4 * n].view(torch.float32).view(rows.value, cols.value).clone()
+
+
+# ---- thin wrappers over the per-kernel entry points (used by tests and profiling) ---------------
+def _dt(t):
+    return {torch.float32: EDV_F32, torch.bfloat16: EDV_BF16, torch.float16: EDV_F16}[t.dtype]
+
+
+def op_linear(A, W, bias=None, act=0, engine=ENGINE_TC):
+    lib = load_library()
+    M, K = A.shape
+    N = W.shape[0]
+    C = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    _check(lib.edv_op_linear(_dt(A), engine, _ptr(A), _ptr(W), _ptr(bias), _ptr(C), M, N, K, act, _stream()), None, "edv_op_linear")
+    return C
+
+
+def op_conv3x3(X, Wt, bias=None, relu_out=False, engine=ENGINE_TC):
+    lib = load_library()
+    F, H, W, Cin = X.shape
+    Cout = Wt.shape[0]
+    Y = torch.empty(F, H, W, Cout, dtype=X.dtype, device=X.device)
+    _check(lib.edv_op_conv3x3(_dt(X), engine, _ptr(X), _ptr(Wt), _ptr(bias), _ptr(Y), F, H, W, Cin, Cout, int(relu_out), _stream()),
+           None, "edv_op_conv3x3")
+    return Y
+
+
+def op_attention(qkv, F, S, heads, engine=ENGINE_TC):
+    lib = load_library()
+    out = torch.empty(F * S, heads * 64, dtype=qkv.dtype, device=qkv.device)
+    _check(lib.edv_op_attention(_dt(qkv), engine, _ptr(qkv), _ptr(out), F, S, heads, _stream()), None, "edv_op_attention")
+    return out
+
+
+def op_temporal_attention(qkv, B, T, hw, C):
+    lib = load_library()
+    out = torch.empty(B * T * hw, C, dtype=qkv.dtype, device=qkv.device)
+    _check(lib.edv_op_temporal_attention(_dt(qkv), _ptr(qkv), _ptr(out), B, T, hw, C, _stream()), None, "edv_op_temporal_attention")
+    return out
+
+
+def op_layernorm(X, gamma, beta, eps, out_dtype):
+    lib = load_library()
+    M, D = X.shape
+    Y = torch.empty(M, D, dtype=out_dtype, device=X.device)
+    _check(lib.edv_op_layernorm(_dt(Y), _ptr(X), _ptr(gamma), _ptr(beta), _ptr(Y), M, D, ctypes.c_float(eps), _stream()), None,
+           "edv_op_layernorm")
+    return Y
+
+
+def op_groupnorm(X, gamma, beta, eps):
+    lib = load_library()
+    F, hw, C = X.shape
+    Y = torch.empty_like(X)
+    _check(lib.edv_op_groupnorm(_dt(X), _ptr(X), _ptr(gamma), _ptr(beta), _ptr(Y), F, hw, C, ctypes.c_float(eps), _stream()), None,
+           "edv_op_groupnorm")
+    return Y
+
+
+def op_upsample(X, oh, ow):
+    lib = load_library()
+    F, h, w, C = X.shape
+    Y = torch.empty(F, oh, ow, C, dtype=X.dtype, device=X.device)
+    _check(lib.edv_op_upsample(_dt(X), _ptr(X), _ptr(Y), F, h, w, oh, ow, C, _stream()), None, "edv_op_upsample")
+    return Y
+
+
+def op_resize_f32(X, oh, ow):
+    lib = load_library()
+    F, h, w = X.shape
+    Y = torch.empty(F, oh, ow, dtype=torch.float32, device=X.device)
+    _check(lib.edv_op_resize_f32(_ptr(X), _ptr(Y), F, h, w, oh, ow, _stream()), None, "edv_op_resize_f32")
+    return Y

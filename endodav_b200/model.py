@@ -1,0 +1,343 @@
+"""Drop-in boundary: the ``endodav`` model class of the reference (models/endodav/endodav.py:52-160)
+re-hosted on the sm_100a engine.
+
+What stays byte-compatible with the reference:
+  * the constructor keyword arguments and their defaults (endodav.py:53-73);
+  * ``state_dict()`` keys, shapes and buffers (``pos_encoder.pe``), so checkpoints written by
+    ``trainer_end_to_end_video.py:1094-1115`` load with ``load_state_dict`` / the key-filtering
+    idiom of ``evaluate_depth_video.py:91-93``;
+  * attributes ``.pretrained``, ``.head``, ``.head.motion_modules`` (trainer...:337-339);
+  * ``forward(x[B,T,3,H,W]) -> {("disp", s): [B*T,1,h_s,w_s]}`` and
+    ``infer_video_depth(frames[N,H,W,3] uint8) -> float32 [N,H,W]``.
+
+What is different: the sub-modules are parameter containers only.  The arithmetic runs in
+hand-written CUDA kernels behind the C ABI (include/endodav_b200.h); there is no PyTorch or
+CPU fallback -- calling ``forward`` without the built library or without an sm_100 GPU raises.
+Inference only (the reference's training loop is out of scope).
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+from . import pack as _pack
+from . import video as _video
+
+_MODEL_SIZES = {
+    "vits": dict(dim=384, depth=12, heads=6, pos_tokens=37 * 37 + 1, taps=[2, 5, 8, 11]),
+    "vitl": dict(dim=1024, depth=24, heads=16, pos_tokens=16 * 16 + 1, taps=[4, 11, 17, 23]),
+}
+
+
+# -----------------------------------------------------------------------------------------
+# parameter layout
+# -----------------------------------------------------------------------------------------
+def _lora_entries(prefix, n_in, n_out, lora_type, r):
+    ents = [(prefix + ".weight", (n_out, n_in), "linear"), (prefix + ".bias", (n_out,), "zeros")]
+    if lora_type == "ssb":
+        ents += [(prefix + ".lora_A", (n_in, 1), "ones"), (prefix + ".lora_B", (n_out, 1), "ones")]
+    elif lora_type in ("lora", "dvlora", "dash"):
+        ents += [(prefix + ".lora_A", (r, n_in), "kaiming"), (prefix + ".lora_B", (n_out, r), "zeros")]
+        if lora_type == "dvlora":
+            ents += [(prefix + ".lora_U", (r, 1), "kaiming"), (prefix + ".lora_V", (n_out, 1), "kaiming")]
+        if lora_type == "dash":
+            ents += [(prefix + ".lora_index", (8,), "zeros"), (prefix + ".weight_u_top", (n_out, 8), "zeros"),
+                     (prefix + ".weight_vt_top", (8, n_in), "zeros")]
+    return ents
+
+
+def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_type, residual_block_indexes,
+                     temporal_lora, disable_conv_head):
+    """Ordered ``[(state_dict key, shape, init kind)]`` reproducing the reference's checkpoint
+    layout.  ``init kind`` is only used for fresh random models."""
+    sz = _MODEL_SIZES[encoder]
+    D, F, oc = sz["dim"], features, list(out_channels)
+    L = []
+    p = "pretrained."
+    L += [(p + "cls_token", (1, 1, D), "tiny"), (p + "pos_embed", (1, sz["pos_tokens"], D), "trunc02"),
+          (p + "mask_token", (1, D), "zeros"), (p + "patch_embed.proj.weight", (D, 3, 14, 14), "kaiming"),
+          (p + "patch_embed.proj.bias", (D,), "zeros")]
+    for i in range(sz["depth"]):
+        b = p + "blocks.%d." % i
+        L += [(b + "norm1.weight", (D,), "ones"), (b + "norm1.bias", (D,), "zeros"),
+              (b + "attn.qkv.weight", (3 * D, D), "trunc02"), (b + "attn.qkv.bias", (3 * D,), "zeros"),
+              (b + "attn.proj.weight", (D, D), "trunc02"), (b + "attn.proj.bias", (D,), "zeros"),
+              (b + "ls1.gamma", (D,), "ls"), (b + "norm2.weight", (D,), "ones"), (b + "norm2.bias", (D,), "zeros")]
+        L += _lora_entries(b + "mlp.fc1", D, 4 * D, lora_type, r)
+        L += _lora_entries(b + "mlp.fc2", 4 * D, D, lora_type, r)
+        L += [(b + "ls2.gamma", (D,), "ls")]
+        if i in residual_block_indexes:
+            bc = D // 8
+            rb = b + "residual_."
+            L += [(rb + "conv1.weight", (bc, D, 1, 1), "kaiming"), (rb + "norm1.weight", (bc,), "ones"),
+                  (rb + "norm1.bias", (bc,), "zeros"), (rb + "conv2.weight", (bc, bc, 3, 3), "kaiming"),
+                  (rb + "norm2.weight", (bc,), "ones"), (rb + "norm2.bias", (bc,), "zeros"),
+                  (rb + "conv3.weight", (D, bc, 1, 1), "kaiming"), (rb + "norm3.weight", (D,), "zeros"),
+                  (rb + "norm3.bias", (D,), "zeros")]
+    L += [(p + "norm.weight", (D,), "ones"), (p + "norm.bias", (D,), "zeros")]
+    h = "head."
+    for i in range(4):
+        L += [(h + "projects.%d.weight" % i, (oc[i], D, 1, 1), "kaiming"), (h + "projects.%d.bias" % i, (oc[i],), "zeros")]
+    L += [(h + "resize_layers.0.weight", (oc[0], oc[0], 4, 4), "kaiming"), (h + "resize_layers.0.bias", (oc[0],), "zeros"),
+          (h + "resize_layers.1.weight", (oc[1], oc[1], 2, 2), "kaiming"), (h + "resize_layers.1.bias", (oc[1],), "zeros"),
+          (h + "resize_layers.3.weight", (oc[3], oc[3], 3, 3), "kaiming"), (h + "resize_layers.3.bias", (oc[3],), "zeros")]
+    s = h + "scratch."
+    for i in range(4):
+        L += [(s + "layer%d_rn.weight" % (i + 1), (F, oc[i], 3, 3), "kaiming")]
+    for k in range(1, 5):
+        rn = s + "refinenet%d." % k
+        L += [(rn + "out_conv.weight", (F, F, 1, 1), "kaiming"), (rn + "out_conv.bias", (F,), "zeros")]
+        for u in (1, 2):
+            for c in (1, 2):
+                L += [(rn + "resConfUnit%d.conv%d.weight" % (u, c), (F, F, 3, 3), "kaiming"),
+                      (rn + "resConfUnit%d.conv%d.bias" % (u, c), (F,), "zeros")]
+    if disable_conv_head:
+        L += [(s + "output_conv1.weight", (F // 2, F, 3, 3), "kaiming"), (s + "output_conv1.bias", (F // 2,), "zeros"),
+              (s + "output_conv2.0.weight", (32, F // 2, 3, 3), "kaiming"), (s + "output_conv2.0.bias", (32,), "zeros"),
+              (s + "output_conv2.2.weight", (1, 32, 1, 1), "kaiming"), (s + "output_conv2.2.bias", (1,), "zeros")]
+    for j, C in enumerate([oc[2], oc[3], F, F]):
+        t = h + "motion_modules.%d.temporal_transformer." % j
+        L += [(t + "norm.weight", (C,), "ones"), (t + "norm.bias", (C,), "zeros"),
+              (t + "proj_in.weight", (C, C), "kaiming"), (t + "proj_in.bias", (C,), "zeros")]
+        tb = t + "transformer_blocks.0."
+        for a in range(2):
+            ab = tb + "attention_blocks.%d." % a
+            L += [(ab + "to_q.weight", (C, C), "kaiming"), (ab + "to_k.weight", (C, C), "kaiming"),
+                  (ab + "to_v.weight", (C, C), "kaiming"), (ab + "to_out.0.weight", (C, C), "kaiming"),
+                  (ab + "to_out.0.bias", (C,), "zeros")]
+            if pe == "ape":
+                L += [(ab + "pos_encoder.pe", (1, num_frames, C), "buffer_pe")]
+        for a in range(2):
+            L += [(tb + "norms.%d.weight" % a, (C,), "ones"), (tb + "norms.%d.bias" % a, (C,), "zeros")]
+        L += [(tb + "ff.net.0.proj.weight", (8 * C, C), "kaiming"), (tb + "ff.net.0.proj.bias", (8 * C,), "zeros")]
+        L += _lora_entries(tb + "ff.net.2", 4 * C, C, lora_type if temporal_lora else "none", r)
+        L += [(tb + "ff_norm.weight", (C,), "ones"), (tb + "ff_norm.bias", (C,), "zeros"),
+              (t + "proj_out.weight", (C, C), "zeros"), (t + "proj_out.bias", (C,), "zeros")]  # zero_module, motion_module.py:57-58
+    if not disable_conv_head:
+        for k in range(1, 5):
+            c = h + "conv_depth_%d.head." % k
+            L += [(c + "0.weight", (F // 2, F, 3, 3), "kaiming"), (c + "0.bias", (F // 2,), "zeros"),
+                  (c + "2.weight", (32, F // 2, 3, 3), "kaiming"), (c + "2.bias", (32,), "zeros"),
+                  (c + "4.weight", (1, 32, 1, 1), "kaiming"), (c + "4.bias", (1,), "zeros")]
+    return L
+
+
+def _init_tensor(shape, kind):
+    if kind == "zeros":
+        return torch.zeros(shape)
+    if kind == "ones":
+        return torch.ones(shape)
+    if kind == "ls":
+        return torch.full(shape, 1e-5)  # LayerScale init_values (vision_transformer.py:360)
+    if kind == "tiny":
+        return torch.randn(shape) * 1e-6
+    if kind == "trunc02":
+        return nn.init.trunc_normal_(torch.empty(shape), std=0.02)
+    if kind in ("kaiming", "linear"):
+        t = torch.empty(shape)
+        if t.dim() < 2:
+            return t.zero_()
+        return nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+    raise ValueError(kind)
+
+
+def _sinusoid(d_model, max_len):
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+class _Holder(nn.Module):
+    """Parameter container mirroring one reference sub-module; holds weights, computes nothing."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("endodav_b200 sub-modules are parameter containers; call the top-level model")
+
+
+def _attach(root, key, tensor, is_buffer):
+    parts = key.split(".")
+    mod = root
+    for i, name in enumerate(parts[:-1]):
+        nxt = mod._modules.get(name)
+        if nxt is None:
+            nxt = _Holder()
+            mod.add_module(name, nxt)
+        mod = nxt
+    if is_buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def _listify(mod):
+    """Containers whose children are all integer-named behave like nn.ModuleList (indexable)."""
+    for name, child in list(mod._modules.items()):
+        _listify(child)
+        names = list(child._modules.keys())
+        if names and all(n.isdigit() for n in names) and not child._parameters and not child._buffers:
+            ml = nn.ModuleList()
+            # keep sparse indices (resize_layers has no '2', output_conv2 no '1') addressable by key
+            dense = names == [str(i) for i in range(len(names))]
+            if dense:
+                for n in names:
+                    ml.append(child._modules[n])
+                mod._modules[name] = ml
+
+
+class endodav(nn.Module):
+    INFER_LEN = _video.INFER_LEN
+    OVERLAP = _video.OVERLAP
+    KEYFRAMES = _video.KEYFRAMES
+    INTERP_LEN = _video.INTERP_LEN
+
+    def __init__(
+        self,
+        encoder='vitl',
+        features=256,
+        out_channels=[256, 512, 1024, 1024],
+        use_bn=False,
+        use_clstoken=False,
+        num_frames=32,
+        pe='ape',
+        # endodav settings
+        r=4,
+        image_shape=(224, 280),
+        lora_type="lora",
+        pretrained_path=None,
+        residual_block_indexes=[],
+        include_cls_token=True,
+        inv_sigmoid=False,
+        temporal_lora=False,
+        disable_conv_head=False,
+        out_sigmoid=False,
+        # endodav_b200 extension (keyword-only in spirit): compute dtype of the CUDA path
+        dtype=None,
+    ):
+        super().__init__()
+        if encoder not in _MODEL_SIZES:
+            raise KeyError(encoder)  # the reference indexes its backbone table the same way (endodav.py:80-91)
+        if use_bn:
+            raise NotImplementedError("use_bn=True is not used by any reference script and is not built")
+        if use_clstoken:
+            raise NotImplementedError("use_clstoken=True (readout projects) is not used by the reference and is not built")
+        if not include_cls_token:
+            raise NotImplementedError("include_cls_token=False is not built")
+        if lora_type not in ("none", "lora", "dvlora", "ssb", "dash"):
+            raise ValueError("unknown lora_type %r" % (lora_type,))
+        if pe not in ("ape", "rope"):
+            raise NotImplementedError(pe)
+        self.encoder = encoder
+        self.image_shape = tuple(image_shape)
+        self.r = r
+        self.intermediate_layer_idx = {'vits': [2, 5, 8, 11], 'vitl': [4, 11, 17, 23]}
+        self._cfg = dict(encoder=encoder, features=features, out_channels=list(out_channels), num_frames=num_frames,
+                         pe=pe, r=r, lora_type=lora_type, residual_block_indexes=list(residual_block_indexes),
+                         temporal_lora=temporal_lora, disable_conv_head=disable_conv_head)
+        self._inv_sigmoid = bool(inv_sigmoid)
+        self._out_sigmoid = bool(out_sigmoid)
+        self._dtype_name = (dtype or os.environ.get("ENDODAV_DTYPE", "bf16")).lower()
+        if self._dtype_name not in _engine.DTYPES:
+            raise ValueError("dtype must be one of %s" % sorted(_engine.DTYPES))
+        self._engine_kind = {"tc": _engine.ENGINE_TC, "simt": _engine.ENGINE_SIMT}[os.environ.get("ENDODAV_ENGINE", "tc").lower()]
+        for key, shape, kind in parameter_layout(**self._cfg):
+            if kind == "buffer_pe":
+                _attach(self, key, _sinusoid(shape[2], shape[1]), True)
+            else:
+                _attach(self, key, _init_tensor(shape, kind), False)
+        _listify(self)
+        self._eng = None
+        self._packed_versions = None
+        self._pos_key = None
+        if pretrained_path is not None:
+            print("load pretrained weight from {}\n".format(pretrained_path))
+            path = os.path.join(pretrained_path, "video_depth_anything_{}.pth".format(self.encoder))
+            self.load_state_dict(torch.load(path, map_location="cpu"), strict=False)
+
+    # -- engine plumbing --------------------------------------------------------------------
+    def _edv_config(self):
+        sz = _MODEL_SIZES[self.encoder]
+        c = _engine.EdvConfig()
+        c.dim, c.depth, c.heads = sz["dim"], sz["depth"], sz["heads"]
+        for i in range(4):
+            c.taps[i] = sz["taps"][i]
+            c.out_channels[i] = self._cfg["out_channels"][i]
+        c.features = self._cfg["features"]
+        c.num_frames = self._cfg["num_frames"]
+        c.conv_head = 0 if self._cfg["disable_conv_head"] else 1
+        c.out_sigmoid = int(self._out_sigmoid)
+        c.inv_sigmoid = int(self._inv_sigmoid)
+        rb = 0
+        for i in self._cfg["residual_block_indexes"]:
+            rb |= 1 << i
+        c.res_blocks = rb
+        c.rope = 1 if self._cfg["pe"] == "rope" else 0
+        c.dtype = _engine.DTYPES[self._dtype_name]
+        c.engine = self._engine_kind
+        return c
+
+    def _versions(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _ensure_engine(self, ph, pw):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _engine.EndoDAVError(
+                "endodav_b200 has no CPU path: move the model to a CUDA device first (model.cuda()); got %s" % dev)
+        if self._eng is None or self._eng.device != dev:
+            self._eng = _engine.Engine(self._edv_config(), dev)
+            self._packed_versions = None
+            self._pos_key = None
+        ver = self._versions()
+        if ver != self._packed_versions:
+            sd = self.state_dict()
+            tdt = _engine.TORCH_DTYPE[_engine.DTYPES[self._dtype_name]]
+            self._eng.set_weights(_pack.pack_state_dict(sd, self._cfg, tdt))
+            self._packed_versions = ver
+            self._pos_key = None
+        if self._pos_key != (ph, pw):
+            self._eng.set_weights(_pack.pos_tables(self.state_dict(), self._cfg, ph, pw))
+            self._pos_key = (ph, pw)
+        return self._eng
+
+    def set_compute_dtype(self, dtype):
+        """'bf16' (default), 'fp16' or 'fp32' -- see DESIGN.md for the accuracy of each."""
+        dtype = dtype.lower()
+        if dtype not in _engine.DTYPES:
+            raise ValueError(dtype)
+        if _engine.DTYPES[dtype] != _engine.DTYPES[self._dtype_name]:
+            self._dtype_name = dtype
+            self._eng = None
+        return self
+
+    # -- reference API ------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x):
+        """endodav.forward (endodav.py:150-160): x [B,T,3,H,W] float in [0,1] ->
+        {("disp", s): [B*T,1,h_s,w_s]}, s = 0..3."""
+        if x.dim() != 5 or x.shape[2] != 3:
+            raise ValueError("expected [B,T,3,H,W], got %s" % (tuple(x.shape),))
+        B, T, _, H, W = x.shape
+        h, w = self.image_shape
+        assert h % 14 == 0, f"Input image height {h} is not a multiple of patch height 14"   # patch_embed.py:72
+        assert w % 14 == 0, f"Input image width {w} is not a multiple of patch width: 14"    # patch_embed.py:73
+        eng = self._ensure_engine(h // 14, w // 14)
+        x = x.to(device=eng.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(eng.device):
+            eng.plan(B, T, H, W, h, w)
+            disp, _ = eng.forward(x)
+        return {("disp", s): disp[s] for s in range(4)}
+
+    @torch.no_grad()
+    def infer_video_depth(self, frames, input_size=518, device='cuda'):
+        """endodav.infer_video_depth (endodav.py:162-254).  ``input_size`` is ignored exactly as in
+        the reference (:164-174).  Uses every visible rank when torch.distributed is initialised."""
+        return _video.infer_video_depth(self, frames, device=device)

@@ -1,0 +1,270 @@
+"""Weight packer: reference ``state_dict`` -> the named, kernel-ready tensors the C-ABI
+library consumes (``edv_set_weight``).  Pure host logic (runs on CPU or GPU tensors), so
+it is unit-tested without a GPU.
+
+What is folded at pack time (all exact in real arithmetic, done in float64):
+  * LoRA-family adapters merged into fc1/fc2 (and motion ``ff.net.2`` with temporal_lora):
+      Linear      W + 2 B A                    (endodav.py:111;  mylora/layers.py:148-157)
+      DVLinear    W + (B*V)(A*U)               (endodav.py:108;  mylora/layers.py:384-393)
+      Linear_SSB  A.view(1,in) * W * B         (mylora/layers.py:423-430)
+      DashLinear  W + 2 B A + U_top diag(idx) Vt_top   (mylora/layers.py:553-582, post-warm-up)
+  * LayerScale gamma into attn.proj / mlp.fc2 (layer_scale.py:26-27; block.py:112-115)
+  * q * head_dim**-0.5 into the q rows of qkv (attention.py:60; motion attention.py:187-188)
+  * projects[i] (1x1) composed with resize_layers[i] (ConvTranspose k==stride) for i=0,1
+    into one GEMM whose columns are (ky,kx,c) -> pixel shuffle (dpt.py:60-83)
+  * temporal q|k|v concatenated; (x+pe)W = xW + peW -> per-frame bias table
+    (motion_module.py:189-197,236-237)
+  * GEGLU projection rows paired per 128-column tile [64 value | 64 gate]
+    (motion_module/attention.py:382-384)
+Conv weights go to (out, ky, kx, c) order with channels padded to multiples of 64.
+"""
+import math
+
+import torch
+
+ENCODERS = {
+    "vits": dict(dim=384, depth=12, heads=6, taps=[2, 5, 8, 11]),
+    "vitl": dict(dim=1024, depth=24, heads=16, taps=[4, 11, 17, 23]),
+}
+KPATCH = 640
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def merged_linear_weight(sd, prefix, lora_type):
+    w = sd[prefix + ".weight"].double()
+    if lora_type in (None, "none") or (prefix + ".lora_A") not in sd:
+        return w
+    A = sd[prefix + ".lora_A"].double()
+    B = sd[prefix + ".lora_B"].double()
+    if lora_type == "dvlora":
+        U = sd[prefix + ".lora_U"].double()
+        V = sd[prefix + ".lora_V"].double()
+        return w + (B * V) @ (A * U)
+    if lora_type == "lora":
+        return w + 2.0 * (B @ A)
+    if lora_type == "ssb":
+        return A.view(1, -1) * w * B
+    if lora_type == "dash":
+        out = w + 2.0 * (B @ A)
+        key = prefix + ".weight_u_top"
+        if key in sd:
+            out = out + sd[key].double() @ torch.diag(sd[prefix + ".lora_index"].double()) @ sd[prefix + ".weight_vt_top"].double()
+        return out
+    raise ValueError("unknown lora_type %r" % (lora_type,))
+
+
+def _conv3_to_gemm(w, cin_pad, cout_pad=None):
+    """[O, I, 3, 3] -> [O_pad, 9*I_pad] in (ky, kx, c) order."""
+    O, I = w.shape[:2]
+    cout_pad = cout_pad or O
+    out = torch.zeros(cout_pad, 3, 3, cin_pad, dtype=w.dtype)
+    out[:O, :, :, :I] = w.permute(0, 2, 3, 1)
+    return out.reshape(cout_pad, 9 * cin_pad)
+
+
+def _pad_vec(v, n):
+    out = torch.zeros(n, dtype=v.dtype)
+    out[: v.numel()] = v.reshape(-1)
+    return out
+
+
+def _merge_convt(sd, i, k, cpad):
+    """projects[i] (1x1, [oc, D]) followed by ConvTranspose2d(k, stride k) [ic, oc, k, k]
+    -> weight [(ky*k+kx)*cpad + oc, D], bias likewise.  (ConvTranspose2d)"""
+    w1 = sd["head.projects.%d.weight" % i].double().flatten(1)  # [ic, D]
+    b1 = sd["head.projects.%d.bias" % i].double()
+    wt = sd["head.resize_layers.%d.weight" % i].double()         # [ic, oc, k, k]
+    bt = sd["head.resize_layers.%d.bias" % i].double()
+    oc = wt.shape[1]
+    D = w1.shape[1]
+    W = torch.zeros(k * k, cpad, D, dtype=torch.float64)
+    Bv = torch.zeros(k * k, cpad, dtype=torch.float64)
+    for ky in range(k):
+        for kx in range(k):
+            m = wt[:, :, ky, kx].t()                 # [oc, ic]
+            W[ky * k + kx, :oc] = m @ w1
+            Bv[ky * k + kx, :oc] = m @ b1 + bt
+    return W.reshape(k * k * cpad, D), Bv.reshape(-1)
+
+
+def pack_state_dict(sd, cfg, dtype=torch.bfloat16):
+    """Returns ``dict[name] -> tensor`` (matrices in ``dtype``, vectors/tables in float32).
+
+    ``cfg``: dict with encoder, features, out_channels, num_frames, lora_type,
+    temporal_lora, disable_conv_head, residual_block_indexes, pe."""
+    enc = ENCODERS[cfg["encoder"]]
+    D, depth, heads = enc["dim"], enc["depth"], enc["heads"]
+    hd = D // heads
+    F = cfg["features"]
+    Fh = F // 2
+    oc = list(cfg["out_channels"])
+    cp = [round_up(c, 64) for c in oc]
+    lt = cfg.get("lora_type", "none")
+    T = cfg["num_frames"]
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    out = {}
+
+    def mat(name, t):
+        out[name] = t.to(dtype).contiguous()
+
+    def vec(name, t):
+        out[name] = t.to(torch.float32).contiguous()
+
+    p = "pretrained."
+    w = sd[p + "patch_embed.proj.weight"].double().reshape(D, -1)
+    wp = torch.zeros(D, KPATCH, dtype=torch.float64)
+    wp[:, : w.shape[1]] = w
+    mat("patch.w", wp)
+    for i in range(depth):
+        b = p + "blocks.%d." % i
+        n = "blk%d." % i
+        vec(n + "ln1.w", sd[b + "norm1.weight"])
+        vec(n + "ln1.b", sd[b + "norm1.bias"])
+        qw = sd[b + "attn.qkv.weight"].double().clone()
+        qb = sd[b + "attn.qkv.bias"].double().clone()
+        qw[:D] *= hd ** -0.5
+        qb[:D] *= hd ** -0.5
+        mat(n + "qkv.w", qw)
+        vec(n + "qkv.b", qb)
+        g1 = sd[b + "ls1.gamma"].double()
+        mat(n + "proj.w", sd[b + "attn.proj.weight"].double() * g1[:, None])
+        vec(n + "proj.b", sd[b + "attn.proj.bias"].double() * g1)
+        vec(n + "ln2.w", sd[b + "norm2.weight"])
+        vec(n + "ln2.b", sd[b + "norm2.bias"])
+        mat(n + "fc1.w", merged_linear_weight(sd, b + "mlp.fc1", lt))
+        vec(n + "fc1.b", sd[b + "mlp.fc1.bias"])
+        g2 = sd[b + "ls2.gamma"].double()
+        mat(n + "fc2.w", merged_linear_weight(sd, b + "mlp.fc2", lt) * g2[:, None])
+        vec(n + "fc2.b", sd[b + "mlp.fc2.bias"].double() * g2)
+        if i in cfg.get("residual_block_indexes", []):
+            rb = b + "residual_."
+            bc = D // 8
+            bcp = round_up(bc, 64)
+            c1 = torch.zeros(bcp, D, dtype=torch.float64)
+            c1[:bc] = sd[rb + "conv1.weight"].double().flatten(1)
+            mat(n + "res.c1.w", c1)
+            vec(n + "res.n1.w", _pad_vec(sd[rb + "norm1.weight"], bcp))
+            vec(n + "res.n1.b", _pad_vec(sd[rb + "norm1.bias"], bcp))
+            mat(n + "res.c2.w", _conv3_to_gemm(sd[rb + "conv2.weight"].double(), bcp, bcp))
+            vec(n + "res.n2.w", _pad_vec(sd[rb + "norm2.weight"], bcp))
+            vec(n + "res.n2.b", _pad_vec(sd[rb + "norm2.bias"], bcp))
+            c3 = torch.zeros(D, bcp, dtype=torch.float64)
+            c3[:, :bc] = sd[rb + "conv3.weight"].double().flatten(1)
+            mat(n + "res.c3.w", c3)
+            vec(n + "res.n3.w", sd[rb + "norm3.weight"])
+            vec(n + "res.n3.b", sd[rb + "norm3.bias"])
+    vec("norm.w", sd[p + "norm.weight"])
+    vec("norm.b", sd[p + "norm.bias"])
+
+    h = "head."
+    W0, B0 = _merge_convt(sd, 0, 4, cp[0])
+    mat("proj0.w", W0)
+    vec("proj0.b", B0)
+    W1, B1 = _merge_convt(sd, 1, 2, cp[1])
+    mat("proj1.w", W1)
+    vec("proj1.b", B1)
+    for i in (2, 3):
+        wi = torch.zeros(cp[i], D, dtype=torch.float64)
+        wi[: oc[i]] = sd[h + "projects.%d.weight" % i].double().flatten(1)
+        mat("proj%d.w" % i, wi)
+        vec("proj%d.b" % i, _pad_vec(sd[h + "projects.%d.bias" % i], cp[i]))
+    mat("resize3.w", _conv3_to_gemm(sd[h + "resize_layers.3.weight"].double(), cp[3], cp[3]))
+    vec("resize3.b", _pad_vec(sd[h + "resize_layers.3.bias"], cp[3]))
+    s = h + "scratch."
+    for i in range(4):
+        mat("rn%d.w" % (i + 1), _conv3_to_gemm(sd[s + "layer%d_rn.weight" % (i + 1)].double(), cp[i]))
+    for k in range(1, 5):
+        rn = s + "refinenet%d." % k
+        n = "ref%d." % k
+        mat(n + "out.w", sd[rn + "out_conv.weight"].double().flatten(1))
+        vec(n + "out.b", sd[rn + "out_conv.bias"])
+        for u in (1, 2):
+            for c in (1, 2):
+                mat(n + "rcu%d.c%d.w" % (u, c), _conv3_to_gemm(sd[rn + "resConfUnit%d.conv%d.weight" % (u, c)].double(), F))
+                vec(n + "rcu%d.c%d.b" % (u, c), sd[rn + "resConfUnit%d.conv%d.bias" % (u, c)])
+
+    def head(c0, c2, c4, k0, k2, k4):
+        mat(c0 + ".w", _conv3_to_gemm(sd[k0 + ".weight"].double(), F))
+        vec(c0 + ".b", sd[k0 + ".bias"])
+        mat(c2 + ".w", _conv3_to_gemm(sd[k2 + ".weight"].double(), Fh))
+        vec(c2 + ".b", sd[k2 + ".bias"])
+        vec(c4 + ".w", torch.cat([sd[k4 + ".weight"].double().reshape(-1), sd[k4 + ".bias"].double().reshape(-1)]))
+
+    if cfg.get("disable_conv_head", False):
+        head("oc1", "oc2a", "oc2b", s + "output_conv1", s + "output_conv2.0", s + "output_conv2.2")
+    else:
+        for k in range(1, 5):
+            c = h + "conv_depth_%d.head." % k
+            head("cd%d.c0" % k, "cd%d.c2" % k, "cd%d.c4" % k, c + "0", c + "2", c + "4")
+
+    mm_ch = [oc[2], oc[3], F, F]
+    tl = lt if cfg.get("temporal_lora", False) else "none"
+    for j in range(4):
+        C = mm_ch[j]
+        thd = C // 8
+        t = h + "motion_modules.%d.temporal_transformer." % j
+        n = "mm%d." % j
+        vec(n + "gn.w", sd[t + "norm.weight"])
+        vec(n + "gn.b", sd[t + "norm.bias"])
+        mat(n + "pin.w", sd[t + "proj_in.weight"])
+        vec(n + "pin.b", sd[t + "proj_in.bias"])
+        tb = t + "transformer_blocks.0."
+        for a in range(2):
+            ab = tb + "attention_blocks.%d." % a
+            an = n + "a%d." % a
+            vec(an + "ln.w", sd[tb + "norms.%d.weight" % a])
+            vec(an + "ln.b", sd[tb + "norms.%d.bias" % a])
+            qkv = torch.cat([sd[ab + "to_q.weight"].double() * thd ** -0.5, sd[ab + "to_k.weight"].double(),
+                             sd[ab + "to_v.weight"].double()], 0)
+            mat(an + "qkv.w", qkv)
+            if cfg.get("pe", "ape") == "ape":
+                pe = sd[ab + "pos_encoder.pe"].double()[0, :T]      # [T, C]
+                vec(an + "petab", pe @ qkv.t())
+            mat(an + "out.w", sd[ab + "to_out.0.weight"])
+            vec(an + "out.b", sd[ab + "to_out.0.bias"])
+        vec(n + "ffln.w", sd[tb + "ff_norm.weight"])
+        vec(n + "ffln.b", sd[tb + "ff_norm.bias"])
+        gw = sd[tb + "ff.net.0.proj.weight"].double()
+        gb = sd[tb + "ff.net.0.proj.bias"].double()
+        C4 = 4 * C
+        idx = []
+        for blk in range(C4 // 64):
+            idx += list(range(blk * 64, blk * 64 + 64)) + list(range(C4 + blk * 64, C4 + blk * 64 + 64))
+        idx = torch.tensor(idx)
+        mat(n + "geglu.w", gw[idx])
+        vec(n + "geglu.b", gb[idx])
+        mat(n + "ff2.w", merged_linear_weight(sd, tb + "ff.net.2", tl))
+        vec(n + "ff2.b", sd[tb + "ff.net.2.bias"])
+        mat(n + "pout.w", sd[t + "proj_out.weight"])
+        vec(n + "pout.b", sd[t + "proj_out.bias"])
+    return out
+
+
+def pos_tables(sd, cfg, ph, pw):
+    """Shape-dependent encoder tables: ``patch.pos`` [ph*pw, D] = interpolated pos-embed of the
+    patch tokens + patch-embed bias, and ``cls_row`` [D] = cls_token + pos[0].
+
+    The interpolation repeats the reference's own torch call (vision_transformer.py:186-217):
+    bicubic, align_corners=False, scale_factor=((ph+0.1)/sqrt(N0), (pw+0.1)/sqrt(N0)), with
+    the raw-table short-circuit when the grid already matches."""
+    import torch.nn.functional as Fn
+
+    pos = sd["pretrained.pos_embed"].detach().float().cpu()
+    n0 = pos.shape[1] - 1
+    dim = pos.shape[-1]
+    if not (ph * pw == n0 and ph == pw):
+        s = int(math.sqrt(n0))
+        sx, sy = float(ph + 0.1) / math.sqrt(n0), float(pw + 0.1) / math.sqrt(n0)
+        patch = Fn.interpolate(pos[:, 1:].reshape(1, s, s, dim).permute(0, 3, 1, 2), scale_factor=(sx, sy),
+                               mode="bicubic", antialias=False)
+        if patch.shape[-2] != ph or patch.shape[-1] != pw:
+            raise ValueError("pos-embed interpolation produced %s, expected (%d,%d)" % (tuple(patch.shape[-2:]), ph, pw))
+        patch = patch.permute(0, 2, 3, 1).reshape(-1, dim)
+    else:
+        patch = pos[0, 1:]
+    bias = sd["pretrained.patch_embed.proj.bias"].detach().float().cpu()
+    cls = sd["pretrained.cls_token"].detach().float().cpu().reshape(-1) + pos[0, 0]
+    return {"patch.pos": (patch + bias[None, :]).contiguous(), "cls_row": cls.contiguous()}

@@ -1,0 +1,213 @@
+"""Sliding-window long-video driver (re-host of ``endodav.infer_video_depth``,
+models/endodav/endodav.py:162-254) with windows sharded across the GPUs of one box.
+
+Reference behaviour that is preserved exactly:
+  * 32-frame windows, stride 22, 10 overlap slots fed from the previous window's *input*
+    slots KEYFRAMES=[6,12,24..31] (endodav.py:47-50,193-199);
+  * per-frame aspect-keeping cubic resize on the host (util/transform.py:62-122);
+  * per-window bilinear resize of the disparity back to the frame size (endodav.py:205);
+  * sequential scale/shift alignment + 8-frame linear cross-fade on rank 0 in float32 numpy,
+    op for op (endodav.py:213-254; utils/util.py:40-74).
+
+What is new: window inputs are a pure function of (k, N), so windows
+are independent.  Rank r of W runs windows k = r, r+W, ... and one NCCL gather moves the
+per-window disparity to rank 0 (``torch.distributed``); there is no collective inside the
+network.  With torch.distributed not initialised this is the single-GPU path.
+"""
+import numpy as np
+import torch
+
+INFER_LEN = 32
+OVERLAP = 10
+KEYFRAMES = [6, 12, 24, 25, 26, 27, 28, 29, 30, 31]
+INTERP_LEN = 8
+STEP = INFER_LEN - OVERLAP
+
+
+def num_windows(n_frames):
+    return (n_frames + STEP - 1) // STEP
+
+
+def window_frame_indices(k, n_frames):
+    """Closed form of the source frame of every slot of window k.
+
+    Unrolling endodav.py:185-199: slot i of window k>0 is slot KEYFRAMES[i] of window k-1 for
+    i<10; KEYFRAMES[2:] = 24..31 are fresh slots of window k-1 (frames 22(k-1)+24.. = 22k+2..),
+    while KEYFRAMES[0:2] = 6,12 are themselves fresh slots of window k-1 when k-1>0
+    (22(k-1)+6 = 22k-16, 22(k-1)+12 = 22k-10) and plain frames 6,12 when k-1 == 0 (same
+    formula).  Padding replicates the last frame, hence the clamp."""
+    idx = np.empty(INFER_LEN, dtype=np.int64)
+    if k == 0:
+        idx[:] = np.arange(INFER_LEN)
+    else:
+        idx[0] = STEP * k - 16
+        idx[1] = STEP * k - 10
+        idx[2:] = STEP * k + np.arange(2, INFER_LEN)
+    return np.minimum(idx, n_frames - 1)
+
+
+def shard_windows(n_windows, rank, world):
+    """Round-robin window ownership: rank r owns k = r, r+world, ...  (SURVEY.md section 8(e))."""
+    return list(range(rank, n_windows, world))
+
+
+def resize_target(width, height, want_w, want_h, multiple=14):
+    """Output size of the reference's Resize(keep_aspect_ratio=True, 'lower_bound',
+    ensure_multiple_of=14) (util/transform.py:49-107)."""
+    scale_h, scale_w = want_h / height, want_w / width
+    if scale_w > scale_h:
+        scale_h = scale_w
+    else:
+        scale_w = scale_h
+
+    def fit(x, lo):
+        y = int(np.round(x / multiple) * multiple)
+        if y < lo:
+            y = int(np.ceil(x / multiple) * multiple)
+        return y
+
+    return fit(scale_w * width, want_w), fit(scale_h * height, want_h)
+
+
+def lsq_scale_shift(pred, target):
+    """compute_scale_and_shift_full with an all-ones mask, float32 numpy sums
+    (utils/util.py:40-62); det == 0 -> (1, 0)."""
+    pred = pred.astype(np.float32)
+    target = target.astype(np.float32)
+    ones = np.ones_like(target, dtype=np.float32)
+    a00 = np.sum(ones * pred * pred)
+    a01 = np.sum(ones * pred)
+    a11 = np.sum(ones)
+    b0 = np.sum(ones * pred * target)
+    b1 = np.sum(ones * target)
+    det = a00 * a11 - a01 * a01
+    if det != 0:
+        return (a11 * b0 - a01 * b1) / det, (-a01 * b0 + a00 * b1) / det
+    return 1, 0
+
+
+def stitch_windows(windows, n_frames):
+    """windows: sequence over k of float32 [32,H,W] -> float32 [n_frames,H,W].
+
+    Sequential by construction: (scale, shift) of window k is fitted against the already
+    aligned tail of windows < k (endodav.py:231-244)."""
+    fade = [0.0] + [i * (1.0 / (INTERP_LEN - 1)) for i in range(1, INTERP_LEN - 1)] + [1.0]
+    seq = []
+    for k, win in enumerate(windows):
+        if k == 0:
+            seq.extend(win[i] for i in range(INFER_LEN))
+            continue
+        pre = seq[-INTERP_LEN:]
+        post = [win[i] for i in range(OVERLAP - INTERP_LEN, OVERLAP)]
+        scale, shift = lsq_scale_shift(np.concatenate(post), np.concatenate(pre))
+        aligned_post = []
+        for f in post:
+            g = f * scale + shift
+            g[g < 0] = 0
+            aligned_post.append(g)
+        seq[-INTERP_LEN:] = [pre[i] * (1 - fade[i]) + aligned_post[i] * fade[i] for i in range(INTERP_LEN)]
+        for i in range(OVERLAP, INFER_LEN):
+            g = win[i] * scale + shift
+            g[g < 0] = 0
+            seq.append(g)
+    return np.stack(seq[:n_frames], axis=0)
+
+
+class _FrameCache:
+    """Host-side preprocessing of the reference (endodav.py:195): float32/255 -> cv2 cubic
+    resize -> CHW.  Each source frame is resized once even when several windows read it."""
+
+    def __init__(self, frames, new_w, new_h):
+        import cv2
+
+        self.cv2 = cv2
+        self.frames = frames
+        self.size = (new_w, new_h)
+        self.cache = {}
+
+    def get(self, idx):
+        t = self.cache.get(idx)
+        if t is None:
+            img = self.frames[idx].astype(np.float32) / 255.0
+            img = self.cv2.resize(img, self.size, interpolation=self.cv2.INTER_CUBIC)
+            t = np.ascontiguousarray(np.transpose(img, (2, 0, 1))).astype(np.float32)
+            self.cache[idx] = t
+        return t
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def infer_video_depth(model, frames, device="cuda", forward_window=None, distributed=True):
+    """frames: uint8 [N,H,W,3] -> float32 [N,H,W] on rank 0 (other ranks return None).
+
+    ``forward_window(clip[1,32,3,h,w] float32 tensor, (H,W)) -> [32,H,W] float32 tensor`` can be
+    injected by tests (index/stitch logic on CPU); by default it is the model's CUDA engine
+    with the final resize fused into the same launch sequence."""
+    frames = np.asarray(frames)
+    if frames.ndim != 4 or frames.shape[-1] != 3:
+        raise ValueError("frames must be [N,H,W,3], got %s" % (frames.shape,))
+    n, H, W = frames.shape[:3]
+    ih, iw = model.image_shape
+    new_w, new_h = resize_target(W, H, iw, ih)
+    cache = _FrameCache(frames, new_w, new_h)
+    dist, rank, world = _dist() if distributed else (None, 0, 1)
+    nwin = num_windows(n)
+    mine = shard_windows(nwin, rank, world)
+
+    if forward_window is None:
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("endodav_b200 has no CPU path (device=%r)" % (device,))
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if next(model.parameters()).device != dev:
+            model.to(dev)
+        eng = model._ensure_engine(ih // 14, iw // 14)
+        # two pinned staging buffers: the host fills window j+1 while the GPU runs window j
+        pinned = [torch.empty(1, INFER_LEN, 3, new_h, new_w, dtype=torch.float32).pin_memory() for _ in range(2)]
+        copied = [None, None]
+        local = []
+        with torch.cuda.device(dev):
+            eng.plan(1, INFER_LEN, new_h, new_w, ih, iw)
+            for j, k in enumerate(mine):
+                slot = j & 1
+                if copied[slot] is not None:
+                    copied[slot].synchronize()  # the earlier H2D copy out of this buffer has finished
+                buf = pinned[slot]
+                for i, src in enumerate(window_frame_indices(k, n)):
+                    buf[0, i].copy_(torch.from_numpy(cache.get(int(src))))
+                x = buf.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                copied[slot] = ev
+                _, resized = eng.forward(x, resize_to=(H, W), want_pyramid=False)
+                local.append(resized)
+        local_t = torch.stack(local, 0) if local else torch.empty(0, INFER_LEN, H, W, dtype=torch.float32, device=dev)
+    else:
+        local = []
+        for k in mine:
+            clip = torch.from_numpy(np.stack([cache.get(int(i)) for i in window_frame_indices(k, n)], 0)).unsqueeze(0)
+            local.append(forward_window(clip, (H, W)).reshape(INFER_LEN, H, W).float())
+        local_t = torch.stack(local, 0) if local else torch.empty(0, INFER_LEN, H, W, dtype=torch.float32)
+
+    if world == 1:
+        wins = local_t.cpu().numpy()
+        return stitch_windows([wins[i] for i in range(nwin)], n)
+
+    # one gather of per-window disparity to rank 0 (padded to the largest shard)
+    per = (nwin + world - 1) // world
+    pad = torch.zeros(per, INFER_LEN, H, W, dtype=torch.float32, device=local_t.device)
+    pad[: local_t.shape[0]] = local_t
+    gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, gathered, dst=0)
+    if rank != 0:
+        return None
+    host = [g.cpu().numpy() for g in gathered]
+    wins = [host[k % world][k // world] for k in range(nwin)]
+    return stitch_windows(wins, n)

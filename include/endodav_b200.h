@@ -1,0 +1,154 @@
+/*
+ * endodav_b200 -- C ABI of the B200-native (sm_100a) EndoDAV video-depth forward path.
+ *
+ * The reference (Zanue/EndoDAV) has no FFI of its own: its boundary for this path is the
+ * Python class `endodav` (models/endodav/endodav.py:52-160).  This header is the thin
+ * C-ABI extension that the Python host class `endodav_b200.endodav` binds with ctypes;
+ * each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative edv_status; never throws;
+ *   - all pointers called *_dev are CUDA device pointers owned by the caller (the Python
+ *     host allocates them with torch); the library never allocates activation memory;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - no global state, no internal threads; one edv_ctx per (device, model).
+ *   - dtype: EDV_F32 runs fp32 CUDA-core kernels (the "tight" path); EDV_BF16 / EDV_F16
+ *     run the tcgen05 tensor-core kernels with 16-bit operands and fp32 accumulation.
+ */
+#ifndef ENDODAV_B200_H
+#define ENDODAV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct edv_ctx edv_ctx;
+
+enum edv_status {
+  EDV_OK = 0,
+  EDV_ERR_ARG = -1,      /* bad argument / unsupported shape */
+  EDV_ERR_CUDA = -2,     /* a CUDA runtime / driver call failed (see edv_last_error) */
+  EDV_ERR_WEIGHT = -3,   /* a required packed weight is missing or has the wrong size */
+  EDV_ERR_STATE = -4,    /* call order violated (e.g. forward before plan) */
+  EDV_ERR_NO_DEVICE = -5 /* no sm_100 device */
+};
+
+enum edv_dtype { EDV_F32 = 0, EDV_BF16 = 1, EDV_F16 = 2 };
+
+/* Which matmul engine a 16-bit ctx uses.  EDV_ENGINE_TC (tcgen05/TMEM/TMA) is the product
+ * path; EDV_ENGINE_SIMT exists so tests can cross-check the tensor-core kernels against the
+ * CUDA-core ones on identical 16-bit operands.  EDV_F32 always uses the SIMT kernels. */
+enum edv_engine { EDV_ENGINE_TC = 0, EDV_ENGINE_SIMT = 1 };
+
+/* Model hyper-parameters: mirrors the constructor of the reference class
+ * (models/endodav/endodav.py:53-73) after resolving the encoder table
+ * (models/backbones/vision_transformer.py:351-398). */
+typedef struct edv_config {
+  int32_t dim;             /* ViT embed dim: 384 (vits) / 1024 (vitl) */
+  int32_t depth;           /* 12 / 24 */
+  int32_t heads;           /* 6 / 16 (head dim must be 64) */
+  int32_t taps[4];         /* block indices tapped: {2,5,8,11} / {4,11,17,23} (endodav.py:76-79) */
+  int32_t features;        /* DPT features: 64 / 256 */
+  int32_t out_channels[4]; /* {48,96,192,384} / {256,512,1024,1024} */
+  int32_t num_frames;      /* temporal_max_len (<= 32) */
+  int32_t conv_head;       /* 0: output_conv1/2 path (disable_conv_head=True); 1: HeadDepth x4 */
+  int32_t out_sigmoid;     /* dpt_pyramid.py:98-102 */
+  int32_t inv_sigmoid;     /* dpt_pyramid.py:105 */
+  int32_t res_blocks;      /* bit i set: ViT block i has a ResBottleneckBlock (block.py:146-150) */
+  int32_t rope;            /* 0: sinusoidal APE table folded into the q|k|v bias; 1: RoPE */
+  int32_t dtype;           /* edv_dtype */
+  int32_t engine;          /* edv_engine */
+} edv_config;
+
+/* --- context ---------------------------------------------------------------------------- */
+
+/* Replaces: endodav.__init__ + .cuda() (endodav.py:53-147; evaluate_depth_video.py:84-95). */
+int edv_create(const edv_config* cfg, edv_ctx** out);
+void edv_destroy(edv_ctx* ctx);
+const char* edv_last_error(const edv_ctx* ctx); /* ctx may be NULL: last creation error */
+
+/* Register one packed weight tensor (device pointer, borrowed until replaced/destroy).
+ * Names and layouts are produced by endodav_b200/pack.py (LoRA merged, LayerScale and
+ * q-scale folded, channels padded, conv weights in (ky,kx,c) order).
+ * Replaces: load_state_dict (evaluate_depth_video.py:91-93). */
+int edv_set_weight(edv_ctx* ctx, const char* name, const void* dev_ptr, size_t bytes);
+
+/* Shape-specialise for clips [B,T,3,H,W] run at network resolution (net_h,net_w)
+ * (= image_shape, multiples of 14).  Returns the workspace size the caller must supply. */
+int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, size_t* workspace_bytes);
+
+/* Replaces: endodav.forward (endodav.py:150-160).
+ *   frames_dev : [B,T,3,H,W] float32 in [0,1]  (NCHW per frame, as the reference takes it)
+ *   disp_dev[s]: [B*T,1,h_s,w_s] float32, s = 0..3 (any may be NULL to skip writing it);
+ *                sizes from edv_output_shape.
+ *   resized_dev: optional [B*T, out_h, out_w] float32 -- disp0 bilinearly resized
+ *                (align_corners=True) to (out_h,out_w): the per-window resize of
+ *                infer_video_depth (endodav.py:205); NULL to skip. */
+int edv_forward(edv_ctx* ctx, const float* frames_dev, float* const disp_dev[4], float* resized_dev, int out_h,
+                int out_w, void* workspace_dev, void* stream);
+
+/* As edv_forward, but frames are uint8 [B*T,H,W,3] (what infer_video_depth receives,
+ * endodav.py:162,195) already at network resolution: x/255 -> normalise -> patches. */
+int edv_forward_u8(edv_ctx* ctx, const uint8_t* frames_dev, float* const disp_dev[4], float* resized_dev, int out_h,
+                   int out_w, void* workspace_dev, void* stream);
+
+int edv_output_shape(const edv_ctx* ctx, int scale, int* h, int* w);
+
+/* Number of kernels the last edv_forward launched (bench.py's gpu_launches). */
+int edv_launch_count(const edv_ctx* ctx);
+
+/* Debug / parity taps.  edv_set_debug(ctx,1) before edv_plan makes edv_forward keep float32
+ * snapshots of the stages the oracle records ("tokens0","block0","tap0".."tap3","layer1".."layer4",
+ * "mm0","mm1","path4_pre","path3","path1"; NHWC / token-major, real channels only) inside the
+ * caller's workspace; edv_debug_tap returns where. */
+int edv_set_debug(edv_ctx* ctx, int on);
+int edv_debug_tap(edv_ctx* ctx, const char* name, size_t* offset_bytes, long long* rows, int* cols);
+
+/* --- per-kernel entry points (unit parity tests + ncu) ---------------------------------- */
+
+/* C[M,N] = A[M,K] * W[N,K]^T (+bias) with optional activation; A,W,C in `dtype`
+ * (fp32 accumulate).  act: 0 none, 1 GELU(erf), 2 ReLU.  engine as in edv_config.
+ * Replaces: every nn.Linear / 1x1 conv on the path (attention.py:58,67; mlp.py:34-37; ...). */
+int edv_op_linear(int dtype, int engine, const void* A, const void* W, const float* bias, void* C, int M, int N, int K,
+                  int act, void* stream);
+
+/* 3x3 convolution, padding 1, stride 1, NHWC: X[F,H,W,Cin] * Wt[Cout, 9*Cin] (+bias),
+ * pre_relu applies ReLU to X first (ResidualConvUnit, util/blocks.py:78-84).
+ * Replaces: scratch.layer*_rn, resConfUnit convs, output_conv1 (dpt.py:100-117). */
+int edv_op_conv3x3(int dtype, int engine, const void* X, const void* Wt, const float* bias, void* Y, int F, int H,
+                   int W, int Cin, int Cout, int relu_out, void* stream);
+
+/* Spatial multi-head attention over token-major qkv [F*S, 3*heads*64] (q pre-scaled) ->
+ * out [F*S, heads*64].  Replaces: Attention.forward's softmax(qk^T)v (attention.py:60-66). */
+int edv_op_attention(int dtype, int engine, const void* qkv, void* out, int F, int S, int heads, void* stream);
+
+/* Temporal attention over the frame axis: qkv [B*T*hw, 3C] (q pre-scaled by hd^-0.5) ->
+ * out [B*T*hw, C]; 8 heads; one softmax per (clip, position, head) over T<=32 frames.
+ * Replaces: TemporalAttention/CrossAttention._attention (motion_module.py:232-295;
+ * motion_module/attention.py:182-211). */
+int edv_op_temporal_attention(int dtype, const void* qkv, void* out, int B, int T, int hw, int C, void* stream);
+
+/* LayerNorm over the last dim: X[M,D] float32 -> Y[M,D] `dtype`. */
+int edv_op_layernorm(int dtype, const float* X, const float* gamma, const float* beta, void* Y, int M, int D,
+                     float eps, void* stream);
+
+/* GroupNorm(32 groups) over NHWC X[F,hw,C] (`dtype`) -> Y same layout.
+ * Replaces: TemporalTransformer3DModel.norm (motion_module.py:84,110). */
+int edv_op_groupnorm(int dtype, const void* X, const float* gamma, const float* beta, void* Y, int F, int hw, int C,
+                     float eps, void* stream);
+
+/* Bilinear resize, align_corners=True, NHWC `dtype`: X[F,h,w,C] -> Y[F,oh,ow,C].
+ * Replaces: F.interpolate calls at util/blocks.py:156-158, dpt_pyramid.py:90-92. */
+int edv_op_upsample(int dtype, const void* X, void* Y, int F, int h, int w, int oh, int ow, int C, void* stream);
+
+/* Bilinear resize of single-channel float32 maps (align_corners=True): disp pyramid
+ * (dpt_pyramid.py:95-97) and the final resize of infer_video_depth (endodav.py:205). */
+int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int ow, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENDODAV_B200_H */
