@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the EndoDAV video-depth forward on B200 (BASELINE.json metric:
+frames/sec on 32-frame 518 px clips at 1/2/4/8 GPUs, with roofline fractions).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+A step is one ``endodav.forward`` over one synthetic 32-frame 518x518 clip per GPU (ViT-S,
+DV-LoRA, bf16 tensor-core path) -- BASELINE.json configs[1].  At N > 1 every rank runs its own
+window (the long-video driver shards independent 32-frame windows) and each
+step ends with the NCCL gather of the per-window disparity to rank 0: weak scaling.
+
+Prints ONE JSON line on rank 0 (see the keys at the bottom of main()).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: ctor kwargs, (B, T, H, W)
+    "vits_518_t32": (dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
+                          image_shape=(518, 518), disable_conv_head=True, residual_block_indexes=[]), (1, 32, 518, 518)),
+    "vits_224x280_t32": (dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
+                              image_shape=(224, 280), disable_conv_head=True, residual_block_indexes=[]), (1, 32, 224, 280)),
+    "vits_224x280_t8": (dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
+                             image_shape=(224, 280), disable_conv_head=True, residual_block_indexes=[]), (1, 8, 224, 280)),
+    "vitl_518_t32": (dict(encoder="vitl", features=256, out_channels=[256, 512, 1024, 1024], r=4, lora_type="dvlora",
+                          image_shape=(518, 518), disable_conv_head=True, residual_block_indexes=[]), (1, 32, 518, 518)),
+}
+METRIC = "frames/sec, 32-frame 518px clips"
+UNIT = "frames/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm), reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------------------------
+# reference algorithm on the host (oracle/ is test infrastructure: only this leg may run it)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_fps(ctor, shape, sample_frames, steps, warmup):
+    import torch
+
+    from oracle import endodav_oracle as orc
+    from oracle import weights
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = weights.full_cfg({k: v for k, v in ctor.items() if k != "image_shape"})
+    sd = weights.make_state_dict(cfg, 1234)
+    B, T, H, W = shape
+    t = min(sample_frames, T)
+    x = weights.make_frames(1, t, H, W, 4321)
+    with torch.no_grad():
+        for _ in range(warmup):
+            orc.forward(sd, x[:, :1], cfg, ctor["image_shape"])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.forward(sd, x, cfg, ctor["image_shape"])
+        dt = time.perf_counter() - t0
+    return dict(value=t * steps / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%d of %d frames of the %dx%d clip per step, %d step(s), fp32 torch CPU restatement of the reference "
+                       "(oracle/endodav_oracle.py), %.1f s" % (t, T, H, W, steps, dt)), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ctor, shape = WORKLOADS[args.workload]
+    base, dt = cpu_reference_fps(ctor, shape, args.cpu_frames, max(1, args.steps), min(args.warmup, 1))
+    steps = max(1, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": "reference algorithm (CPU port) on host cores; each step is a bounded sample"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vits_518_t32", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-out", default=None, help="write the per-call-site kernel table (JSON) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import endodav_b200 as E
+    from endodav_b200 import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the sm_100a path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    ctor, (B, T, H, Wd) = WORKLOADS[args.workload]
+    model = E.endodav(dtype=args.dtype, **ctor)
+    synthetic.randomize_(model, 1234)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(4321 + rank)
+    host = torch.rand(B, T, 3, H, Wd, generator=g).pin_memory()
+    x = host.to(dev)
+    frames_per_step = B * T
+
+    gather_bufs = None
+    side = torch.cuda.Stream()
+
+    def step(inp):
+        out = model(inp)
+        d0 = out[("disp", 0)]
+        if world > 1:
+            # the one collective of the path: per-window disparity -> rank 0
+            dist.gather(d0, gather_bufs if rank == 0 else None, dst=0)
+        return d0
+
+    if world > 1 and rank == 0:
+        oh, ow = ctor["image_shape"]
+        gather_bufs = [torch.empty(B * T, 1, oh, ow, dtype=torch.float32, device=dev) for _ in range(world)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        d0 = step(x)
+    eng = model._eng
+    launches_per_step = eng.launch_count()
+    ws_gb = eng.workspace.numel() / 1e9
+
+    # ---- timed region: K steps, inputs resident in HBM ---------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        d0 = step(x)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * frames_per_step * K / (ms * 1e-3)
+
+    # ---- same K steps with one CUDA event per launch: per-kernel device time ---------------------
+    eng.profile(True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(K):
+        model(x)
+    p1.record()
+    torch.cuda.synchronize()
+    prof_ms = p0.elapsed_time(p1)
+    table = eng.profile_collect()
+    eng.profile(False)
+
+    # ---- end to end through the public API with HOST buffers -------------------------------------
+    out_host = torch.empty(B * T, 1, *ctor["image_shape"], dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        out_host.copy_(step(host.to(dev, non_blocking=True)), non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        xin = host.to(dev, non_blocking=True)
+        out_host.copy_(step(xin), non_blocking=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_val = world * frames_per_step * K / float(t_e.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks = measured_peaks()
+    table.sort(key=lambda r: -r["ms"])
+    tot = sum(r["ms"] for r in table) or 1.0
+    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    for r in table:
+        r["share"] = r["ms"] / tot
+        r["avg_us"] = 1e3 * r["ms"] / max(1, r["count"])
+        r["tflops"] = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else 0.0
+        r["gbs"] = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0.0
+        r["bound"] = "tensor" if (r["bytes"] > 0 and r["flops"] / r["bytes"] >= ridge) else "hbm"
+    top = table[0] if table else None
+    roofline = None
+    if top:
+        if top["bound"] == "tensor":
+            roofline = dict(kernel=top["name"], bound="tensor", achieved=top["tflops"], peak=peaks["bf16_tflops_sustained"],
+                            unit="TFLOP/s", frac=top["tflops"] / peaks["bf16_tflops_sustained"])
+        else:
+            roofline = dict(kernel=top["name"], bound="hbm", achieved=top["gbs"], peak=peaks["hbm_gbs"], unit="GB/s",
+                            frac=top["gbs"] / peaks["hbm_gbs"])
+        roofline.update(traffic=None, share_of_step=top["share"], avg_launch_us=top["avg_us"], launches_per_step=top["count"] // K,
+                        peak_source=peaks["source"] + (", sustained bf16" if top["bound"] == "tensor" else ""))
+        # whole-forward tensor utilisation: all contraction FLOPs / step time
+        roofline["step_tflops"] = sum(r["flops"] for r in table) / K / (ms / K * 1e-3) / 1e12
+    if args.kernels_out:
+        with open(args.kernels_out, "w") as f:
+            json.dump(dict(workload=args.workload, steps=K, profiled_ms_per_step=prof_ms / K, ms_per_step=ms / K, kernels=table), f, indent=1)
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_fps(ctor, (B, T, H, Wd), args.cpu_frames, 1, 1)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": args.workload, "clips_per_gpu_per_step": B, "frames_per_clip": T, "frame": [H, Wd],
+                   "network_resolution": list(ctor["image_shape"]), "weights": "random-init, de-degenerated (endodav_b200/synthetic.py)",
+                   "l2": "no flush: per-step working set %.2f GB of activations >> 126 MB L2" % ws_gb,
+                   "parallelism": "window-sharded dp%d + NCCL gather to rank 0" % world if world > 1 else "single GPU"},
+        "roofline": roofline, "cpu_baseline": cpu_base,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launches_per_step * K * world, "clocks": clocks,
+        "profiled_ms_per_step": prof_ms / K,
+        "top_kernels": [dict(name=r["name"], share=round(r["share"], 4), avg_us=round(r["avg_us"], 1), tflops=round(r["tflops"], 1),
+                             gbs=round(r["gbs"], 1)) for r in table[:8]],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -66,6 +66,13 @@ struct edv_ctx {
   int last_launches = 0;
   int debug = 0;
   int Kp = 640;
+  Profiler prof;
+  struct Agg {
+    double ms = 0, flops = 0, bytes = 0;
+    long long count = 0;
+  };
+  std::map<std::string, Agg> prof_agg;
+  std::vector<std::string> prof_names;  // stable order for edv_profile_get
 };
 
 namespace {
@@ -81,6 +88,7 @@ struct Fwd {
 
   Fwd(edv_ctx* ctx, void* workspace, cudaStream_t s) : c(ctx), ws((unsigned char*)workspace) {
     L.stream = s;
+    L.prof = &ctx->prof;
     dt = ctx->cfg.dtype;
     eng = ctx->cfg.dtype == EDV_F32 ? EDV_ENGINE_SIMT : ctx->cfg.engine;
     es = dtype_size(dt);
@@ -112,19 +120,32 @@ struct Fwd {
   const float* wf(const std::string& name, size_t n) { return (const float*)w(name, n * 4); }
   const void* wt(const std::string& name, size_t n) { return w(name, n * es); }
 
+  // call-site tag for the profiler: the packed weight name without indices ("blk3.qkv.w" -> "blk.qkv")
+  static std::string tag_of(const std::string& wname) {
+    std::string t;
+    for (char ch : wname)
+      if (ch < '0' || ch > '9') t.push_back(ch);
+    if (t.size() > 2 && t.compare(t.size() - 2, 2, ".w") == 0) t.resize(t.size() - 2);
+    return t;
+  }
+
   // ---- building blocks --------------------------------------------------------------------
   void linear(const void* A, long long M, int K, const std::string& wname, int N, Epi e) {
     GemmArgs a;
     a.A = A; a.W = wt(wname, (size_t)N * K); a.M = (int)M; a.N = N; a.K = K; a.lda = K; a.e = e;
     if (!L.ok()) return;
+    L.tag = tag_of(wname);
     gemm(L, dt, eng, a);
+    L.tag.clear();
   }
   void conv3(const void* X, int F, int H, int Wd, int C, const std::string& wname, int N, Epi e) {
     GemmArgs a;
     a.A = X; a.W = wt(wname, (size_t)N * 9 * C); a.M = F * H * Wd; a.N = N; a.K = 9 * C; a.e = e;
     a.conv = true; a.F = F; a.H = H; a.Wd = Wd; a.C = C; a.stride = 1;
     if (!L.ok()) return;
+    L.tag = tag_of(wname);
     gemm(L, dt, eng, a);
+    L.tag.clear();
   }
   Epi ep(void* out, long long ldo, const float* bias) {
     Epi e = epi_zero();
@@ -283,12 +304,14 @@ struct Fwd {
     const Plan& p = c->plan;
     const edv_config& g = c->cfg;
     const int D = g.dim;
+    L.begin();
     // ---- K1 + K2: preprocess, patch embedding (patch_embed.py:75-77; vision_transformer.py:219-227)
     void* A0 = buf("A0");
     float* x = (float*)buf("x");
     {
       long long tot = p.Mp * KPATCH;
       unsigned blocks = nblk(tot, 256);
+      L.note(0, (double)p.BT * 3 * p.H * p.W * (u8 ? 1 : 4) + (double)tot * es);
       EDV_DISPATCH_T(dt, {
         if (u8) preprocess_patches_kernel<T, true><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH);
         else preprocess_patches_kernel<T, false><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH);
@@ -738,6 +761,63 @@ int edv_debug_tap(edv_ctx* ctx, const char* name, size_t* offset_bytes, long lon
   *offset_bytes = it->second.buf.off;
   *rows = it->second.rows;
   *cols = it->second.cols;
+  return EDV_OK;
+}
+
+// ---- live per-launch timing (bench.py roofline) --------------------------------------------
+int edv_profile(edv_ctx* ctx, int on) {
+  if (!ctx) return EDV_ERR_ARG;
+  ctx->prof.on = on != 0;
+  return EDV_OK;
+}
+
+int edv_profile_reset(edv_ctx* ctx) {
+  if (!ctx) return EDV_ERR_ARG;
+  ctx->prof.used = 0;
+  ctx->prof.recs.clear();
+  ctx->prof_agg.clear();
+  ctx->prof_names.clear();
+  return EDV_OK;
+}
+
+// Wait for the recorded events and fold them into per-call-site totals.  Returns the number
+// of distinct call sites (>= 0) or a negative status.
+int edv_profile_collect(edv_ctx* ctx) {
+  if (!ctx) return EDV_ERR_ARG;
+  Profiler& pr = ctx->prof;
+  if (pr.used) {
+    if (cudaEventSynchronize(pr.ev[pr.used - 1]) != cudaSuccess) return set_err(ctx, EDV_ERR_CUDA, "edv_profile_collect: event sync failed");
+    for (size_t i = 1; i < pr.used; ++i) {
+      const ProfRec& r = pr.recs[i];
+      if (r.name.empty()) continue;  // start marker of a forward
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.ev[i - 1], pr.ev[i]) != cudaSuccess) continue;
+      auto it = ctx->prof_agg.find(r.name);
+      if (it == ctx->prof_agg.end()) {
+        ctx->prof_names.push_back(r.name);
+        it = ctx->prof_agg.emplace(r.name, edv_ctx::Agg()).first;
+      }
+      it->second.ms += ms;
+      it->second.flops += r.flops;
+      it->second.bytes += r.bytes;
+      it->second.count += 1;
+    }
+  }
+  pr.used = 0;
+  pr.recs.clear();
+  return (int)ctx->prof_names.size();
+}
+
+int edv_profile_get(edv_ctx* ctx, int index, char* name, int name_cap, double* ms, long long* count, double* flops,
+                    double* bytes) {
+  if (!ctx || index < 0 || index >= (int)ctx->prof_names.size() || !name || name_cap < 1) return EDV_ERR_ARG;
+  const std::string& n = ctx->prof_names[index];
+  const edv_ctx::Agg& a = ctx->prof_agg[n];
+  snprintf(name, name_cap, "%s", n.c_str());
+  if (ms) *ms = a.ms;
+  if (count) *count = a.count;
+  if (flops) *flops = a.flops;
+  if (bytes) *bytes = a.bytes;
   return EDV_OK;
 }
 

@@ -3,16 +3,57 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/endodav_b200.h"
 
 namespace edv {
+
+// Optional per-launch timing: one CUDA event after every launch on the launching stream, so
+// the duration of launch i is event[i] - event[i-1] (the stream is serial).  Used by bench.py
+// for the live roofline numbers; off by default (no events are recorded).
+struct ProfRec {
+  std::string name;   // "" marks the start of a forward
+  double flops, bytes;
+};
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<ProfRec> recs;
+  size_t used = 0;
+  cudaEvent_t next() {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  void mark(cudaStream_t s, const std::string& name, double flops, double bytes) {
+    cudaEventRecord(next(), s);
+    recs.push_back(ProfRec{name, flops, bytes});
+  }
+  ~Profiler() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
 
 struct Launch {
   cudaStream_t stream = nullptr;
   int count = 0;         // kernels launched
   int status = EDV_OK;   // first error
   std::string err;
+  Profiler* prof = nullptr;
+  std::string tag;       // which call site of the forward graph the next launches belong to
+  double nflops = 0, nbytes = 0;  // algorithmic work of the next launch (set by the launcher)
+
+  void note(double flops, double bytes) {
+    nflops = flops;
+    nbytes = bytes;
+  }
+  void begin() {
+    if (prof && prof->on) prof->mark(stream, "", 0, 0);
+  }
 
   void fail(int code, const std::string& what) {
     if (status == EDV_OK) {
@@ -24,6 +65,8 @@ struct Launch {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) fail(EDV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
     ++count;
+    if (prof && prof->on) prof->mark(stream, tag.empty() ? std::string(what) : std::string(what) + ":" + tag, nflops, nbytes);
+    nflops = nbytes = 0;
   }
   bool ok() const { return status == EDV_OK; }
 };

@@ -93,7 +93,14 @@ inline Epi epi_zero() {
   return e;
 }
 
+inline void note_gemm(Launch& L, const GemmArgs& a, size_t es) {
+  // algorithmic work: 2*M*N*K; bytes: A (conv: the activation once) + W + C once
+  const double a_elems = a.conv ? (double)a.F * a.H * a.Wd * a.C : (double)a.M * a.K;
+  L.note(2.0 * a.M * a.N * a.K, (a_elems + (double)a.N * a.K + (double)a.M * a.N) * es);
+}
+
 template <typename T> void launch_gemm_simt(Launch& L, const GemmArgs& a) {
+  note_gemm(L, a, sizeof(T));
   dim3 grid((a.N + SG_BN - 1) / SG_BN, (unsigned)((a.M + SG_BM - 1) / SG_BM));
   ConvGeom g{};
   if (a.conv) {
@@ -165,6 +172,7 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
     attr_done = true;
   }
   const long long blocks = m_tiles * (a.N / BN);
+  note_gemm(L, a, 2);
   kern<<<(unsigned)blocks, GT_THREADS, smem, L.stream>>>(tmA, tmB, a.e, a.M, a.N, a.K, stages, ct);
   L.check("gemm_tc");
 }
@@ -225,6 +233,7 @@ inline void layernorm(Launch& L, int dtype, const float* x, const float* g, cons
   if (D % 4 != 0 || D > 1024) return L.fail(EDV_ERR_ARG, "layernorm: D must be a multiple of 4 and <= 1024");
   const int maxv = (D + 127) / 128;
   const unsigned blocks = nblk(Mout * 32, 256);
+  L.note(0, (double)Mout * D * (4 + dtype_size(dtype)));
   EDV_DISPATCH_T(dtype, {
     if (maxv <= 1) layernorm_kernel<T, 1><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
     else if (maxv <= 2) layernorm_kernel<T, 2><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
@@ -240,9 +249,11 @@ inline void groupnorm(Launch& L, int dtype, const void* x, const float* g, const
   if (!L.ok()) return;
   if (C % 32 != 0 || C % 8 != 0) return L.fail(EDV_ERR_ARG, "groupnorm: C must be a multiple of 32");
   EDV_DISPATCH_T(dtype, {
+    L.note(0, (double)F * hw * C * sizeof(T));
     groupnorm_stats_kernel<T><<<dim3(32, F), 256, 0, L.stream>>>((const T*)x, stats, hw, C, eps);
     L.check("groupnorm_stats");
     long long total8 = (long long)F * hw * C / 8;
+    L.note(0, 2.0 * F * hw * C * sizeof(T));
     groupnorm_apply_kernel<T><<<nblk(total8, 256), 256, 0, L.stream>>>((const T*)x, stats, g, b, (T*)y, total8, hw, C);
   });
   L.check("groupnorm_apply");
@@ -252,6 +263,7 @@ inline void upsample(Launch& L, int dtype, const void* x, void* y, int F, int h,
   if (!L.ok()) return;
   if (C % 8 != 0) return L.fail(EDV_ERR_ARG, "upsample: C must be a multiple of 8");
   long long total = (long long)F * oh * ow * (C / 8);
+  L.note(0, ((double)F * h * w + (double)F * oh * ow) * C * dtype_size(dtype));
   EDV_DISPATCH_T(dtype, { upsample_nhwc_kernel<T><<<nblk(total, 256), 256, 0, L.stream>>>((const T*)x, (T*)y, F, h, w, oh, ow, C); });
   L.check("upsample");
 }
@@ -259,12 +271,15 @@ inline void upsample(Launch& L, int dtype, const void* x, void* y, int F, int h,
 inline void resize_f32(Launch& L, const float* x, float* y, int F, int h, int w, int oh, int ow, int sigmoid = 0) {
   if (!L.ok()) return;
   long long total = (long long)F * oh * ow;
+  L.note(0, ((double)F * h * w + (double)F * oh * ow) * 4);
   resize_f32_kernel<<<nblk(total, 256), 256, 0, L.stream>>>(x, y, F, h, w, oh, ow, sigmoid);
   L.check("resize_f32");
 }
 
 inline void attention(Launch& L, int dtype, int engine, const void* qkv, void* out, int F, int S, int heads) {
   if (!L.ok()) return;
+  // QK^T + PV: 4*S*S*64 per (frame, head); q,k,v read once, o written once
+  L.note(4.0 * F * heads * (double)S * S * 64, 4.0 * F * S * heads * 64 * dtype_size(dtype));
   if (dtype != EDV_F32 && engine == EDV_ENGINE_TC) {
     if (dtype == EDV_BF16) tc::launch_attention_tc<bf16>(L, dtype, qkv, out, F, S, heads);
     else tc::launch_attention_tc<f16>(L, dtype, qkv, out, F, S, heads);
@@ -289,6 +304,7 @@ void launch_temporal(Launch& L, const void* qkv, void* out, int B, int Tn, int h
     attr_done = true;
   }
   dim3 grid(hw, B, heads / hpb);
+  L.note(4.0 * B * hw * heads * (double)Tn * Tn * HD, 4.0 * B * Tn * hw * C * sizeof(T));
   kern<<<grid, 32 * hpb, smem, L.stream>>>((const T*)qkv, (T*)out, Tn, hw, C, hpb);
   L.check("temporal_attention");
 }

@@ -20,7 +20,7 @@ EXPORTS = [
     "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
     "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_op_linear", "edv_op_conv3x3",
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
-    "edv_op_resize_f32",
+    "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
 ]
 
 
@@ -65,6 +65,12 @@ def load_library():
     lib.edv_set_debug.argtypes = [vp, ci]
     lib.edv_debug_tap.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_longlong),
                                   ctypes.POINTER(ci)]
+    lib.edv_profile.argtypes = [vp, ci]
+    lib.edv_profile_reset.argtypes = [vp]
+    lib.edv_profile_collect.argtypes = [vp]
+    lib.edv_profile_get.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double)]
     lib.edv_op_linear.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.edv_op_conv3x3.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.edv_op_attention.argtypes = [ci, ci, vp, vp, ci, ci, ci, vp]
@@ -177,6 +183,26 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.edv_launch_count(self.ctx))
+
+    def profile(self, on: bool):
+        """Per-launch CUDA-event timing inside edv_forward (bench.py's live roofline)."""
+        _check(self.lib.edv_profile(self.ctx, int(on)), self.ctx, "edv_profile")
+        if on:
+            _check(self.lib.edv_profile_reset(self.ctx), self.ctx, "edv_profile_reset")
+
+    def profile_collect(self):
+        """-> list of dict(name, ms, count, flops, bytes), totals since profile(True)."""
+        n = self.lib.edv_profile_collect(self.ctx)
+        if n < 0:
+            _check(n, self.ctx, "edv_profile_collect")
+        out = []
+        buf = ctypes.create_string_buffer(128)
+        for i in range(n):
+            ms, cnt, fl, by = ctypes.c_double(0), ctypes.c_longlong(0), ctypes.c_double(0), ctypes.c_double(0)
+            _check(self.lib.edv_profile_get(self.ctx, i, buf, 128, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(fl),
+                                            ctypes.byref(by)), self.ctx, "edv_profile_get")
+            out.append(dict(name=buf.value.decode(), ms=ms.value, count=cnt.value, flops=fl.value, bytes=by.value))
+        return out
 
     def debug_tap(self, name):
         off, rows, cols = ctypes.c_size_t(0), ctypes.c_longlong(0), ctypes.c_int(0)

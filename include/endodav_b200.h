@@ -100,6 +100,17 @@ int edv_output_shape(const edv_ctx* ctx, int scale, int* h, int* w);
 /* Number of kernels the last edv_forward launched (bench.py's gpu_launches). */
 int edv_launch_count(const edv_ctx* ctx);
 
+/* Live per-launch timing for bench.py's roofline numbers.  With edv_profile(ctx,1) every kernel
+ * launch of edv_forward is followed by a CUDA event on the caller's stream; edv_profile_collect
+ * waits for them and accumulates, per call site ("gemm_tc:blk.qkv", "spatial_attention_tc", ...),
+ * the device time, launch count and the algorithmic FLOPs / bytes of DESIGN.md.  Returns the
+ * number of call sites; edv_profile_get reads entry `index`. */
+int edv_profile(edv_ctx* ctx, int on);
+int edv_profile_reset(edv_ctx* ctx);
+int edv_profile_collect(edv_ctx* ctx);
+int edv_profile_get(edv_ctx* ctx, int index, char* name, int name_cap, double* ms, long long* count, double* flops,
+                    double* bytes);
+
 /* Debug / parity taps.  edv_set_debug(ctx,1) before edv_plan makes edv_forward keep float32
  * snapshots of the stages the oracle records ("tokens0","block0","tap0".."tap3","layer1".."layer4",
  * "mm0","mm1","path4_pre","path3","path1"; NHWC / token-major, real channels only) inside the
