@@ -6,7 +6,7 @@ frames/sec on 32-frame 518 px clips at 1/2/4/8 GPUs, with roofline fractions).
   python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
 
 A step is one ``endodav.forward`` over one synthetic 32-frame 518x518 clip per GPU (ViT-S,
-DV-LoRA, bf16 tensor-core path) -- BASELINE.json configs[1].  At N > 1 every rank runs its own
+DV-LoRA, 16-bit tcgen05 path: fp16 operands by default, --dtype bf16 runs the same kernels) -- BASELINE.json configs[1].  At N > 1 every rank runs its own
 window (the long-video driver shards independent 32-frame windows) and each
 step ends with the NCCL gather of the per-window disparity to rank 0: weak scaling.
 
@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vits_518_t32", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels-out", default=None, help="write the per-call-site kernel table (JSON) here")

@@ -241,7 +241,7 @@ class endodav(nn.Module):
                          temporal_lora=temporal_lora, disable_conv_head=disable_conv_head)
         self._inv_sigmoid = bool(inv_sigmoid)
         self._out_sigmoid = bool(out_sigmoid)
-        self._dtype_name = (dtype or os.environ.get("ENDODAV_DTYPE", "bf16")).lower()
+        self._dtype_name = (dtype or os.environ.get("ENDODAV_DTYPE", "fp16")).lower()
         if self._dtype_name not in _engine.DTYPES:
             raise ValueError("dtype must be one of %s" % sorted(_engine.DTYPES))
         self._engine_kind = {"tc": _engine.ENGINE_TC, "simt": _engine.ENGINE_SIMT}[os.environ.get("ENDODAV_ENGINE", "tc").lower()]
@@ -309,7 +309,7 @@ class endodav(nn.Module):
         return self._eng
 
     def set_compute_dtype(self, dtype):
-        """'bf16' (default), 'fp16' or 'fp32' -- see DESIGN.md for the accuracy of each."""
+        """'fp16' (default), 'bf16' or 'fp32' -- see DESIGN.md for the accuracy of each."""
         dtype = dtype.lower()
         if dtype not in _engine.DTYPES:
             raise ValueError(dtype)

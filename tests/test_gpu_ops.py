@@ -193,8 +193,10 @@ def test_upsample_nhwc(dtype, Fr, h, w, oh, ow, C):
 def test_resize_f32(Fr, h, w, oh, ow):
     X = _rand((Fr, h, w), torch.float32, 20)
     got = eng.op_resize_f32(X, oh, ow)
-    ref = F.interpolate(X.double()[:, None], size=(oh, ow), mode="bilinear", align_corners=True)[:, 0].float()
-    _close(got, ref, torch.float32, "resize_f32", slack=4.0)
+    # source coordinates are computed in float32 exactly like ATen's upsample_bilinear2d
+    # (a float64 reference differs by up to 1.4e-4 at 518 -> 259 through the coordinate rounding)
+    ref = F.interpolate(X[:, None], size=(oh, ow), mode="bilinear", align_corners=True)[:, 0]
+    _close(got, ref, torch.float32, "resize_f32", slack=1.0)
 
 
 def test_pyramid_downscale_matches_scale_factor_half():
