@@ -106,6 +106,28 @@ template <typename T, int NV> __device__ __forceinline__ void store_vec(T* __res
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// GELU(erf) for the 16-bit paths: gelu(x) = relu(x) - 0.5 |x| P(t) exp(-x^2/2), t = 1/(1 + p|x|/sqrt2),
+// P the Abramowitz-Stegun 7.1.26 erfc polynomial (|erf error| <= 1.5e-7, far below 16-bit output
+// rounding); written without the 1 - erf cancellation.  2 MUFU + ~12 FMA-pipe instructions
+// instead of erff()'s ~25, which matters because the fc1 epilogue is as long as its mainloop.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x * x * (-0.5f * 1.4426950408889634f)));
+  return fmaf(-0.5f * ax * p, ex, fmaxf(x, 0.f));
+}
+template <typename T> __device__ __forceinline__ float gelu_act(float x) {
+  if constexpr (sizeof(T) == 4) return gelu_erf(x);
+  else return gelu_fast(x);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -153,17 +175,20 @@ __device__ __forceinline__ long long epi_row(const Epi& e, long long m) {
 template <typename T, int NV>
 __device__ __forceinline__ void epi_apply(const Epi& e, long long m, long long orow, int n0, float* v) {
   if (e.bias) {
+    float b[NV];
+    load_vec<float, NV>(e.bias + n0, b);   // n0 is a multiple of 4 at every call site
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += __ldg(e.bias + n0 + i);
+    for (int i = 0; i < NV; ++i) v[i] += b[i];
   }
   if (e.rowbias) {
-    const float* rb = e.rowbias + (long long)((m / e.rb_div) % e.rb_mod) * e.rb_ld + n0;
+    float b[NV];
+    load_vec<float, NV>(e.rowbias + (long long)((m / e.rb_div) % e.rb_mod) * e.rb_ld + n0, b);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += __ldg(rb + i);
+    for (int i = 0; i < NV; ++i) v[i] += b[i];
   }
   if (e.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < NV; ++i) v[i] = gelu_act<T>(v[i]);
   }
   long long ocol = n0;
   if (e.map == MAP_PIXSHUF) {

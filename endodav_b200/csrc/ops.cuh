@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -114,6 +115,16 @@ template <typename T> void launch_gemm_simt(Launch& L, const GemmArgs& a) {
   L.check("gemm_simt");
 }
 
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 // choose the conv tile shape (th*tw == 128) wasting the fewest pixels
 inline void pick_conv_tile(int H, int W, int* th, int* tw) {
   const int cand[6][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {1, 128}};
@@ -160,20 +171,24 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
   }
   const int kblocks = a.K / BK;
   const int stage_bytes = gt_stage_bytes<BN, BK>();
-  int stages = (96 * 1024) / stage_bytes;  // two CTAs per SM
-  if (stages > kblocks) stages = kblocks;
-  if (stages < 2) stages = kblocks < 2 ? 1 : 2;
+  const size_t stg_bytes = 8 * (size_t)GT_STG_WORDS * 4;   // epilogue transposition buffers
+  int stages = (int)((220 * 1024 - stg_bytes - 2048) / stage_bytes);  // one persistent CTA per SM owns the shared memory
   if (stages > 8) stages = 8;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16;
+  if (stages < 2) stages = 2;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 4) * 8 + 16 + stg_bytes;
   auto kern = gemm_tc_kernel<T, BN, BK, CONV>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     attr_done = true;
   }
-  const long long blocks = m_tiles * (a.N / BN);
+  const int n_tiles = a.N / BN;
+  const long long total = m_tiles * n_tiles;
+  if (total > 0x7fffffffLL) return L.fail(EDV_ERR_ARG, "gemm_tc: too many tiles");
+  const int grid = (int)std::min<long long>(total, num_sms());
+  (void)kblocks;
   note_gemm(L, a, 2);
-  kern<<<(unsigned)blocks, GT_THREADS, smem, L.stream>>>(tmA, tmB, a.e, a.M, a.N, a.K, stages, ct);
+  kern<<<grid, GT_THREADS, smem, L.stream>>>(tmA, tmB, a.e, a.M, a.N, a.K, stages, ct, n_tiles, (int)total);
   L.check("gemm_tc");
 }
 
@@ -185,15 +200,20 @@ template <typename T> void launch_gemm_tc(Launch& L, int dtype, const GemmArgs& 
   int bn;
   if (a.e.act == ACT_GEGLU) bn = 128;
   else if (a.e.act == ACT_HEAD) bn = 32;
+  else if (bk == 64 && a.N % 256 == 0) bn = 256;   // wide tiles halve the shared-memory traffic per FLOP
+  else if (bk == 64 && a.N % 192 == 0) bn = 192;
   else bn = (a.N % 128 == 0) ? 128 : (a.N % 64 == 0) ? 64 : 32;
   if (a.N % bn != 0) return L.fail(EDV_ERR_ARG, "gemm_tc: N must be a multiple of 32");
   if (a.e.act == ACT_HEAD && a.N != 32) return L.fail(EDV_ERR_ARG, "gemm_tc: head epilogue needs N == 32");
+  if (a.e.map == MAP_PIXSHUF && (a.e.ps_c % bn != 0 && bn % a.e.ps_c != 0)) bn = 64;
 #define EDV_TC_CASE(BN_, BK_)                                                         \
   if (bn == BN_ && bk == BK_) {                                                       \
     if (a.conv) launch_gemm_tc_inst<T, BN_, BK_, true>(L, dtype, a);                  \
     else launch_gemm_tc_inst<T, BN_, BK_, false>(L, dtype, a);                        \
     return;                                                                           \
   }
+  EDV_TC_CASE(256, 64)
+  EDV_TC_CASE(192, 64)
   EDV_TC_CASE(128, 64)
   EDV_TC_CASE(64, 64)
   EDV_TC_CASE(32, 64)

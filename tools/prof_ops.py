@@ -1,0 +1,36 @@
+"""Runs the hot kernels once each at the BASELINE config-2 shapes through the C ABI (for ncu)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from endodav_b200 import engine as eng  # noqa: E402
+
+dt = torch.float16
+M = 32 * 1370
+g = torch.Generator().manual_seed(0)
+
+
+def rnd(*s, scale=1.0):
+    return (torch.randn(*s, generator=g) * scale).to(dt).cuda()
+
+
+which = sys.argv[1:] or ["fc1", "qkv", "fc2", "attn", "rcu", "tattn"]
+reps = 2
+for w in which:
+    for _ in range(reps):
+        if w == "fc1":
+            eng.op_linear(rnd(M, 384), rnd(1536, 384, scale=0.05), torch.zeros(1536).cuda(), 1)
+        elif w == "qkv":
+            eng.op_linear(rnd(M, 384), rnd(1152, 384, scale=0.05), torch.zeros(1152).cuda(), 0)
+        elif w == "fc2":
+            eng.op_linear(rnd(M, 1536), rnd(384, 1536, scale=0.03), torch.zeros(384).cuda(), 0)
+        elif w == "attn":
+            eng.op_attention(rnd(M, 1152, scale=0.5), 32, 1370, 6)
+        elif w == "rcu":
+            eng.op_conv3x3(rnd(32, 148, 148, 64), rnd(64, 576, scale=0.04), torch.zeros(64).cuda(), True)
+        elif w == "tattn":
+            eng.op_temporal_attention(rnd(32 * 5476, 192, scale=0.7), 1, 32, 5476, 64)
+    torch.cuda.synchronize()
+print("ok")
