@@ -277,8 +277,15 @@ struct Fwd {
     void* o1 = buf("head.o1");
     void* up = buf("head.up");
     conv3(X, p.BT, H, Wd, F_, c0 + ".w", Fh, ep(o1, Fh, wf(c0 + ".b", Fh)));
-    upsample(L, dt, o1, up, p.BT, H, Wd, OH, OW, Fh);
     const float* hw_ = wf(c4 + ".w", 33);
+    if (tc() && head_fused_supported(dt, Fh)) {
+      // K14: the upsampled map and the 32-channel conv output never touch HBM
+      L.tag = tag_of(c2);
+      head_fused(L, dt, o1, wt(c2 + ".w", (size_t)32 * 9 * Fh), wf(c2 + ".b", 32), hw_, out, p.BT, H, Wd, OH, OW, Fh, sig_sign);
+      L.tag.clear();
+      return;
+    }
+    upsample(L, dt, o1, up, p.BT, H, Wd, OH, OW, Fh);
     if (tc()) {
       Epi e = ep(out, 1, wf(c2 + ".b", 32));
       e.act = ACT_HEAD; e.head_w = hw_; e.sig_sign = sig_sign; e.out_f32 = 1;
@@ -864,6 +871,14 @@ int edv_op_temporal_attention(int dtype, const void* qkv, void* out, int B, int 
   Launch L;
   L.stream = (cudaStream_t)stream;
   temporal_attention(L, dtype, qkv, out, B, T, hw, C);
+  return finish(L);
+}
+
+int edv_op_disp_head(int dtype, const void* X, const void* Wt, const float* bias, const float* head_w, float* out, int F,
+                     int H1, int W1, int OH, int OW, int Cin, float sig_sign, void* stream) {
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  head_fused(L, dtype, X, Wt, bias, head_w, out, F, H1, W1, OH, OW, Cin, sig_sign);
   return finish(L);
 }
 

@@ -1,0 +1,190 @@
+// Fused disparity-head tail (the "memory-bound tail" of the forward):
+//   bilinear upsample (align_corners=True) of the F/2-channel map to the output resolution
+//   -> 3x3 conv (F/2 -> 32) + bias -> ReLU -> 1x1 conv (32 -> 1) + bias -> ReLU | sigmoid
+// Replaces dpt_pyramid.py:90-93 + dpt.py:118-124 (output_conv2) and the tail of HeadDepth
+// (models/endodav/layers.py:211-217 + dpt_pyramid.py:104-109).  Unfused, the upsampled map and
+// the 32-channel conv output would make three HBM round trips at the full output resolution
+// (~75 MB / frame at 518^2); fused, the kernel reads the low-resolution map once and writes one
+// float per pixel (6.7 MB / frame).
+//
+// Persistent CTAs, one per SM, loop over 16 x 8 output-pixel tiles (= the 128 rows of one MMA):
+//   warps 0..3   epilogue: tcgen05.ld the 128 x 32 accumulator (lane = pixel), bias/ReLU/dot/ReLU, store
+//   warp  4      TMEM allocator + MMA issuer: 9 taps x (CIN/16) tcgen05.mma (M=128, N=32, K=16);
+//                the A operand of tap (ky,kx) is simply the halo tile read at a shifted start
+//                address -- the halo is stored chunk-planar ([8-channel chunk][pixel] x 16 B), which
+//                IS the canonical no-swizzle K-major UMMA layout for any shift (SBO = halo row pitch)
+//   warps 5..12  producers: compute the 18 x 10 halo of the upsampled map straight into that
+//                shared-memory layout (double buffered), zero outside the image (conv padding)
+#pragma once
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int HF_TH = 16, HF_TW = 8;              // output tile
+constexpr int HF_HH = HF_TH + 2, HF_HW = HF_TW + 2;  // halo
+constexpr int HF_PIX = HF_HH * HF_HW;             // 180
+constexpr int HF_PLANE = HF_PIX * 16;             // bytes per 8-channel chunk plane
+constexpr int HF_THREADS = 13 * 32;
+constexpr int HF_PRODUCERS = 8 * 32;
+
+template <int CIN> constexpr size_t hf_smem_bytes() {
+  return 1024 + (size_t)9 * (CIN / 8) * 512 + 2 * (size_t)(CIN / 8) * HF_PLANE + 256;
+}
+
+template <typename T, int CIN>
+__global__ void __launch_bounds__(HF_THREADS, 1)
+    head_fused_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ head_w, float* __restrict__ out, int F, int H1, int W1, int OH, int OW,
+                      float sig_sign, int tiles_x, int tiles_y, int total_tiles) {
+  constexpr int NCH = CIN / 8;                     // 16-byte channel chunks per pixel
+  constexpr uint32_t W_BYTES = 9 * NCH * 512;
+  constexpr uint32_t HALO_BYTES = NCH * HF_PLANE;
+  extern __shared__ __align__(1024) unsigned char hf_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(hf_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* wsm = smem;
+  unsigned char* halo = smem + W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(halo + 2 * HALO_BYTES);
+  uint64_t* halo_full = bars;       // 2
+  uint64_t* halo_empty = bars + 2;  // 2
+  uint64_t* acc_full = bars + 4;    // 2
+  uint64_t* acc_empty = bars + 6;   // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // weights [32][9*CIN] (ky,kx,c) -> canonical no-swizzle K-major: [tap][chunk][n] x 16 B
+  for (int i = threadIdx.x; i < 9 * NCH * 32; i += HF_THREADS) {
+    const int n = i & 31;
+    const int tc_ = i >> 5;  // tap * NCH + chunk
+    const uint4 v = *reinterpret_cast<const uint4*>(w + (size_t)n * (9 * CIN) + (size_t)tc_ * 8);
+    *reinterpret_cast<uint4*>(wsm + (size_t)tc_ * 512 + n * 16) = v;
+  }
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&halo_full[b], HF_PRODUCERS);
+      mbar_init(&halo_empty[b], 1);
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 128);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async();   // weight stores (generic proxy) -> visible to tcgen05 (async proxy)
+  if (warp == 4) tmem_alloc(tmem_slot, 64);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per_frame = tiles_x * tiles_y;
+
+  if (warp >= 5) {
+    // ===== producers =====
+    const int pt = threadIdx.x - 5 * 32;
+    const float sy = (OH > 1) ? (float)(H1 - 1) / (float)(OH - 1) : 0.f;
+    const float sx = (OW > 1) ? (float)(W1 - 1) / (float)(OW - 1) : 0.f;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1;
+      const int f = tile / per_frame;
+      const int r = tile - f * per_frame;
+      const int ty = r / tiles_x;
+      const int y0t = ty * HF_TH - 1, x0t = (r - ty * tiles_x) * HF_TW - 1;
+      mbar_wait(&halo_empty[b], ((it >> 1) & 1) ^ 1);
+      unsigned char* hb = halo + b * HALO_BYTES;
+      const T* xf = x + (size_t)f * H1 * W1 * CIN;
+      for (int t = pt; t < HF_PIX * NCH; t += HF_PRODUCERS) {
+        const int p = t / NCH, kc = t - p * NCH;
+        const int hy = p / HF_HW, hx = p - hy * HF_HW;
+        const int oy = y0t + hy, ox = x0t + hx;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (oy >= 0 && oy < OH && ox >= 0 && ox < OW) {
+          // identical arithmetic to upsample_nhwc_kernel (elementwise.cuh)
+          const float fy = sy * oy, fx = sx * ox;
+          const int ya = (int)fy, xa = (int)fx;
+          const int yb = min(ya + 1, H1 - 1), xb = min(xa + 1, W1 - 1);
+          const float ly = fy - ya, lx = fx - xa;
+          float a[8], bq[8], cq[8], d[8], v[8];
+          load_vec<T, 8>(xf + ((size_t)ya * W1 + xa) * CIN + kc * 8, a);
+          load_vec<T, 8>(xf + ((size_t)ya * W1 + xb) * CIN + kc * 8, bq);
+          load_vec<T, 8>(xf + ((size_t)yb * W1 + xa) * CIN + kc * 8, cq);
+          load_vec<T, 8>(xf + ((size_t)yb * W1 + xb) * CIN + kc * 8, d);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            v[jj] = (1.f - ly) * ((1.f - lx) * a[jj] + lx * bq[jj]) + ly * ((1.f - lx) * cq[jj] + lx * d[jj]);
+          o.x = pack2(from_f<T>(v[0]), from_f<T>(v[1]));
+          o.y = pack2(from_f<T>(v[2]), from_f<T>(v[3]));
+          o.z = pack2(from_f<T>(v[4]), from_f<T>(v[5]));
+          o.w = pack2(from_f<T>(v[6]), from_f<T>(v[7]));
+        }
+        *reinterpret_cast<uint4*>(hb + (size_t)kc * HF_PLANE + p * 16) = o;
+      }
+      fence_proxy_async();
+      mbar_arrive(&halo_full[b]);
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<T>(128, 32, 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t b = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[b], ph ^ 1);
+        mbar_wait(&halo_full[b], ph);
+        fence_after_sync();
+        const uint32_t ha = smem_u32(halo + b * HALO_BYTES);
+        const uint32_t wa = smem_u32(wsm);
+        uint32_t first = 1;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+#pragma unroll
+          for (int k = 0; k < CIN / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(ha + (2 * k) * HF_PLANE + (ky * HF_HW + kx) * 16, HF_HW * 16, HF_PLANE, 0);
+            const uint64_t bdesc = make_smem_desc(wa + (tap * NCH + 2 * k) * 512, 128, 512, 0);
+            mma_ss(tmem_base + b * 32, adesc, bdesc, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+        }
+        mma_commit(&halo_empty[b]);
+        mma_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp;                 // warps 0..3 own TMEM lane quarters 0..3
+    const int r = q * 32 + lane;
+    const int dy = r >> 3, dx = r & 7;
+    float bv[32], hw_[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { bv[i] = __ldg(bias + i); hw_[i] = __ldg(head_w + i); }
+    const float hb_ = __ldg(head_w + 32);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1;
+      const int f = tile / per_frame;
+      const int rr = tile - f * per_frame;
+      const int ty = rr / tiles_x;
+      const int oy = ty * HF_TH + dy, ox = (rr - ty * tiles_x) * HF_TW + dx;
+      mbar_wait(&acc_full[b], (it >> 1) & 1);
+      fence_after_sync();
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * 32, v);
+      fence_before_sync();
+      mbar_arrive(&acc_empty[b]);
+      if (oy < OH && ox < OW) {
+        float s = hb_;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s = fmaf(fmaxf(v[i] + bv[i], 0.f), hw_[i], s);
+        if (sig_sign == 0.f) s = fmaxf(s, 0.f);
+        else s = 1.f / (1.f + expf(-sig_sign * s));
+        out[((size_t)f * OH + oy) * OW + ox] = s;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+}  // namespace tc

@@ -142,6 +142,13 @@ int edv_op_attention(int dtype, int engine, const void* qkv, void* out, int F, i
  * motion_module/attention.py:182-211). */
 int edv_op_temporal_attention(int dtype, const void* qkv, void* out, int B, int T, int hw, int C, void* stream);
 
+/* Fused disparity-head tail on an NHWC map X[F,H1,W1,Cin] (16-bit, Cin in {32,128}):
+ * bilinear resize (align_corners=True) to (OH,OW) -> 3x3 conv Wt[32, 9*Cin] + bias -> ReLU ->
+ * 1x1 conv head_w[0..31] + head_w[32] -> ReLU (sig_sign == 0) or sigmoid(sig_sign * x) -> out[F,OH,OW] f32.
+ * Replaces dpt_pyramid.py:90-93 + dpt.py:118-124 (output_conv2); layers.py:211-217 (HeadDepth). */
+int edv_op_disp_head(int dtype, const void* X, const void* Wt, const float* bias, const float* head_w, float* out, int F,
+                     int H1, int W1, int OH, int OW, int Cin, float sig_sign, void* stream);
+
 /* LayerNorm over the last dim: X[M,D] float32 -> Y[M,D] `dtype`. */
 int edv_op_layernorm(int dtype, const float* X, const float* gamma, const float* beta, void* Y, int M, int D,
                      float eps, void* stream);
