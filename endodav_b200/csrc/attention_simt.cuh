@@ -98,87 +98,124 @@ __global__ void __launch_bounds__(128) spatial_attention_simt_kernel(const T* __
 // temporal attention
 //   qkv : [B*T*hw, 3C]  row (b*T + f)*hw + d,  columns [q | k | v], head h at h*HD
 //   out : [B*T*hw, C]
-//   grid (hw, B, head_groups); block = 32 * HPB threads (one warp per head of the group)
-// shared memory: q|k|v rows of the T frames for the HPB heads, padded so that lanes
-// (frames) hit different banks when each reads its own row.
+//   grid (ceil(hw/PB), B, 8/HG); block = 32 * HG * PB threads: one warp per (position, head),
+//   lane = query frame.  A CTA owns PB consecutive positions x HG heads:
+//     1. cooperative 16-byte loads of the T frames' q|k|v segments (consecutive positions are
+//        consecutive rows, so each frame contributes one contiguous run per segment); K and V
+//        are converted to fp32 once, q stays in the activation dtype
+//     2. per warp: T x T scores in registers (K rows are shared-memory broadcasts), softmax
+//        without any cross-lane traffic, P.V with V broadcasts
+//     3. the output overwrites the warp's own q slots and leaves through cooperative 16-byte stores
+//   The activation is read once and written once; no rearranged copy exists.
 // ---------------------------------------------------------------------------------------
+template <int HD> constexpr int ta_max_threads() { return HD >= 64 ? 256 : 512; }
+
 template <typename T, int HD>
-__global__ void temporal_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn, int hw, int C,
-                                          int HPB) {
+__global__ void __launch_bounds__(ta_max_threads<HD>()) temporal_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn, int hw, int C, int PB,
+                                          int HG) {
+  constexpr int VEC = 16 / (int)sizeof(T);       // elements per 16-byte chunk
+  constexpr int QPAD = 16 / (int)sizeof(T);      // q rows are padded by 16 B: lanes (frames) read their own row
   extern __shared__ __align__(16) unsigned char tsm_raw[];
-  float* sm = reinterpret_cast<float*>(tsm_raw);
-  const int d = blockIdx.x, b = blockIdx.y, hg = blockIdx.z;
-  const int W3 = 3 * HPB * HD;   // floats per frame row in smem (q|k|v of this head group)
-  const int RS = W3 + 1;         // padded row stride
+  const int W = HG * HD;                         // channels of this head group
+  const int rowKV = PB * W;                      // floats per frame in Ks / Vs
+  const int rowQ = PB * W + QPAD;                // elements per frame in Qs
+  float* Ks = reinterpret_cast<float*>(tsm_raw);
+  float* Vs = Ks + (size_t)Tn * rowKV;
+  T* Qs = reinterpret_cast<T*>(Vs + (size_t)Tn * rowKV);
+  const int d0 = blockIdx.x * PB, b = blockIdx.y, hg = blockIdx.z;
+  const int npos = min(PB, hw - d0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nthreads = blockDim.x;
   const long long ld = 3LL * C;
-  const int c0 = hg * HPB * HD;  // first channel of the head group
-  // cooperative, coalesced load: for each frame, 3 segments (q,k,v) of HPB*HD contiguous elements
-  const int seg = HPB * HD;
-  for (int i = threadIdx.x; i < Tn * 3 * seg; i += nthreads) {
-    int f = i / (3 * seg);
-    int r = i - f * 3 * seg;
-    int which = r / seg, c = r - which * seg;
-    const T* row = qkv + ((long long)(b * Tn + f) * hw + d) * ld + (long long)which * C + c0 + c;
-    sm[f * RS + which * seg + c] = to_f<T>(*row);
-  }
-  __syncthreads();
-  if (warp < HPB) {
-    const int hoff = warp * HD;
-    float s[32];
-    if (lane < Tn) {
-      const float* qrow = sm + lane * RS + hoff;
+  const int c0 = hg * W;
+  const int cpr = W / VEC;                       // 16-byte chunks per (frame, position, segment)
+
+  // ---- 1. load ----
+  const int total = Tn * npos * 3 * cpr;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int c = i % cpr;
+    int r = i / cpr;
+    const int which = r % 3;
+    r /= 3;
+    const int pos = r % npos, f = r / npos;
+    const T* src = qkv + ((long long)(b * Tn + f) * hw + d0 + pos) * ld + (long long)which * C + c0 + c * VEC;
+    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    if (which == 0) {
+      *reinterpret_cast<uint4*>(Qs + (size_t)f * rowQ + pos * W + c * VEC) = raw;
+    } else {
+      float* dst = (which == 1 ? Ks : Vs) + (size_t)f * rowKV + pos * W + c * VEC;
+      const T* e = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) s[j] = 0.f;
-      // scores: q_t . k_j  (k_j broadcast across lanes, q_t conflict-free thanks to the padding)
-#pragma unroll
-      for (int dd = 0; dd < HD; dd += 8) {
-        float qv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) qv[u] = qrow[dd + u];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < Tn) {
-            const float* krow = sm + j * RS + seg + hoff + dd;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s[j] = fmaf(qv[u], krow[u], s[j]);
-          }
-        }
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < Tn) mx = fmaxf(mx, s[j]);
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        s[j] = (j < Tn) ? expf(s[j] - mx) : 0.f;
-        l += s[j];
-      }
-      const float inv = 1.f / l;
-      float o[HD];
-#pragma unroll
-      for (int dd = 0; dd < HD; ++dd) o[dd] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < Tn) {
-          const float* vrow = sm + j * RS + 2 * seg + hoff;
-          const float p = s[j] * inv;
-#pragma unroll
-          for (int dd = 0; dd < HD; ++dd) o[dd] = fmaf(p, vrow[dd], o[dd]);
-        }
-      }
-      // every lane of this warp has finished reading q (its own row) -> reuse the q slot
-      // of the row for the output so the global store below is coalesced.
-      __syncwarp(__activemask());
-      float* orow = sm + lane * RS + hoff;
-#pragma unroll
-      for (int dd = 0; dd < HD; ++dd) orow[dd] = o[dd];
+      for (int u = 0; u < VEC; u += 4)
+        *reinterpret_cast<float4*>(dst + u) = make_float4(to_f<T>(e[u]), to_f<T>(e[u + 1]), to_f<T>(e[u + 2]), to_f<T>(e[u + 3]));
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Tn * seg; i += nthreads) {
-    int f = i / seg, c = i - f * seg;
-    out[((long long)(b * Tn + f) * hw + d) * C + c0 + c] = from_f<T>(sm[f * RS + c]);
+
+  // ---- 2. attention: warp = (position, head), lane = query frame ----
+  const int pos = warp / HG, hl = warp - pos * HG;
+  if (pos < npos && lane < Tn) {
+    const int off = pos * W + hl * HD;
+    const T* qrow = Qs + (size_t)lane * rowQ + off;
+    float s[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s[j] = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < HD; dd += 8) {
+      float qv[8];
+      load_vec<T, 8>(qrow + dd, qv);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < Tn) {
+          const float4 k0 = *reinterpret_cast<const float4*>(Ks + (size_t)j * rowKV + off + dd);
+          const float4 k1 = *reinterpret_cast<const float4*>(Ks + (size_t)j * rowKV + off + dd + 4);
+          float a = s[j];
+          a = fmaf(qv[0], k0.x, a); a = fmaf(qv[1], k0.y, a); a = fmaf(qv[2], k0.z, a); a = fmaf(qv[3], k0.w, a);
+          a = fmaf(qv[4], k1.x, a); a = fmaf(qv[5], k1.y, a); a = fmaf(qv[6], k1.z, a); a = fmaf(qv[7], k1.w, a);
+          s[j] = a;
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < Tn) mx = fmaxf(mx, s[j]);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s[j] = (j < Tn) ? expf(s[j] - mx) : 0.f;
+      l += s[j];
+    }
+    const float inv = 1.f / l;
+    float o[HD];
+#pragma unroll
+    for (int dd = 0; dd < HD; ++dd) o[dd] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < Tn) {
+        const float pj = s[j] * inv;
+        const float* vrow = Vs + (size_t)j * rowKV + off;
+#pragma unroll
+        for (int dd = 0; dd < HD; dd += 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(vrow + dd);
+          o[dd] = fmaf(pj, v4.x, o[dd]); o[dd + 1] = fmaf(pj, v4.y, o[dd + 1]);
+          o[dd + 2] = fmaf(pj, v4.z, o[dd + 2]); o[dd + 3] = fmaf(pj, v4.w, o[dd + 3]);
+        }
+      }
+    }
+    // only this lane ever read these q slots: reuse them for the output
+    T* orow = Qs + (size_t)lane * rowQ + off;
+#pragma unroll
+    for (int dd = 0; dd < HD; dd += 8) store_vec<T, 8>(orow + dd, o + dd);
+  }
+  __syncthreads();
+
+  // ---- 3. store ----
+  const int ototal = Tn * npos * cpr;
+  for (int i = threadIdx.x; i < ototal; i += blockDim.x) {
+    const int c = i % cpr;
+    const int r = i / cpr;
+    const int p2 = r % npos, f = r / npos;
+    *reinterpret_cast<uint4*>(out + ((long long)(b * Tn + f) * hw + d0 + p2) * C + c0 + c * VEC) =
+        *reinterpret_cast<const uint4*>(Qs + (size_t)f * rowQ + p2 * W + c * VEC);
   }
 }

@@ -14,7 +14,7 @@
 //                address -- the halo is stored chunk-planar ([8-channel chunk][pixel] x 16 B), which
 //                IS the canonical no-swizzle K-major UMMA layout for any shift (SBO = halo row pitch)
 //   warps 5..12  producers: compute the 18 x 10 halo of the upsampled map straight into that
-//                shared-memory layout (double buffered), zero outside the image (conv padding)
+//                shared-memory layout (4-deep ring), zero outside the image (conv padding)
 #pragma once
 #include "tc_common.cuh"
 
@@ -26,9 +26,10 @@ constexpr int HF_PIX = HF_HH * HF_HW;             // 180
 constexpr int HF_PLANE = HF_PIX * 16;             // bytes per 8-channel chunk plane
 constexpr int HF_THREADS = 13 * 32;
 constexpr int HF_PRODUCERS = 8 * 32;
+template <int CIN> constexpr int hf_stages() { return CIN <= 32 ? 4 : 2; }   // halo ring depth (shared-memory budget)
 
 template <int CIN> constexpr size_t hf_smem_bytes() {
-  return 1024 + (size_t)9 * (CIN / 8) * 512 + 2 * (size_t)(CIN / 8) * HF_PLANE + 256;
+  return 1024 + (size_t)9 * (CIN / 8) * 512 + hf_stages<CIN>() * (size_t)(CIN / 8) * HF_PLANE + 256;
 }
 
 template <typename T, int CIN>
@@ -39,16 +40,17 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
   constexpr int NCH = CIN / 8;                     // 16-byte channel chunks per pixel
   constexpr uint32_t W_BYTES = 9 * NCH * 512;
   constexpr uint32_t HALO_BYTES = NCH * HF_PLANE;
+  constexpr int HF_STAGES = hf_stages<CIN>();
   extern __shared__ __align__(1024) unsigned char hf_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(hf_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* wsm = smem;
   unsigned char* halo = smem + W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(halo + 2 * HALO_BYTES);
-  uint64_t* halo_full = bars;       // 2
-  uint64_t* halo_empty = bars + 2;  // 2
-  uint64_t* acc_full = bars + 4;    // 2
-  uint64_t* acc_empty = bars + 6;   // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(halo + HF_STAGES * HALO_BYTES);
+  uint64_t* halo_full = bars;                    // HF_STAGES
+  uint64_t* halo_empty = bars + HF_STAGES;       // HF_STAGES
+  uint64_t* acc_full = bars + 2 * HF_STAGES;     // 2
+  uint64_t* acc_empty = acc_full + 2;            // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -60,9 +62,11 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
     *reinterpret_cast<uint4*>(wsm + (size_t)tc_ * 512 + n * 16) = v;
   }
   if (threadIdx.x == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < HF_STAGES; ++b) {
       mbar_init(&halo_full[b], HF_PRODUCERS);
       mbar_init(&halo_empty[b], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 128);
     }
@@ -83,39 +87,62 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
     const float sx = (OW > 1) ? (float)(W1 - 1) / (float)(OW - 1) : 0.f;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t b = it & 1;
+      const uint32_t b = it % HF_STAGES;
       const int f = tile / per_frame;
       const int r = tile - f * per_frame;
       const int ty = r / tiles_x;
       const int y0t = ty * HF_TH - 1, x0t = (r - ty * tiles_x) * HF_TW - 1;
-      mbar_wait(&halo_empty[b], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&halo_empty[b], ((it / HF_STAGES) & 1) ^ 1);
       unsigned char* hb = halo + b * HALO_BYTES;
       const T* xf = x + (size_t)f * H1 * W1 * CIN;
-      for (int t = pt; t < HF_PIX * NCH; t += HF_PRODUCERS) {
-        const int p = t / NCH, kc = t - p * NCH;
-        const int hy = p / HF_HW, hx = p - hy * HF_HW;
-        const int oy = y0t + hy, ox = x0t + hx;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (oy >= 0 && oy < OH && ox >= 0 && ox < OW) {
+      constexpr int NT = 3;   // tasks per batch: all 12 loads are issued before the first use
+      for (int t0 = pt; t0 < HF_PIX * NCH; t0 += NT * HF_PRODUCERS) {
+        uint4 va[NT], vb[NT], vc[NT], vd[NT];
+        float ly[NT], lx[NT];
+        bool in[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+          const int t = t0 + u * HF_PRODUCERS;
+          const int p = t / NCH, kc = t - p * NCH;
+          const int hy = p / HF_HW, hx = p - hy * HF_HW;
+          const int oy = y0t + hy, ox = x0t + hx;
+          in[u] = (t < HF_PIX * NCH) && oy >= 0 && oy < OH && ox >= 0 && ox < OW;
           // identical arithmetic to upsample_nhwc_kernel (elementwise.cuh)
           const float fy = sy * oy, fx = sx * ox;
           const int ya = (int)fy, xa = (int)fx;
           const int yb = min(ya + 1, H1 - 1), xb = min(xa + 1, W1 - 1);
-          const float ly = fy - ya, lx = fx - xa;
-          float a[8], bq[8], cq[8], d[8], v[8];
-          load_vec<T, 8>(xf + ((size_t)ya * W1 + xa) * CIN + kc * 8, a);
-          load_vec<T, 8>(xf + ((size_t)ya * W1 + xb) * CIN + kc * 8, bq);
-          load_vec<T, 8>(xf + ((size_t)yb * W1 + xa) * CIN + kc * 8, cq);
-          load_vec<T, 8>(xf + ((size_t)yb * W1 + xb) * CIN + kc * 8, d);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj)
-            v[jj] = (1.f - ly) * ((1.f - lx) * a[jj] + lx * bq[jj]) + ly * ((1.f - lx) * cq[jj] + lx * d[jj]);
-          o.x = pack2(from_f<T>(v[0]), from_f<T>(v[1]));
-          o.y = pack2(from_f<T>(v[2]), from_f<T>(v[3]));
-          o.z = pack2(from_f<T>(v[4]), from_f<T>(v[5]));
-          o.w = pack2(from_f<T>(v[6]), from_f<T>(v[7]));
+          ly[u] = fy - ya;
+          lx[u] = fx - xa;
+          if (in[u]) {
+            va[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)ya * W1 + xa) * CIN + kc * 8);
+            vb[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)ya * W1 + xb) * CIN + kc * 8);
+            vc[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)yb * W1 + xa) * CIN + kc * 8);
+            vd[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)yb * W1 + xb) * CIN + kc * 8);
+          }
         }
-        *reinterpret_cast<uint4*>(hb + (size_t)kc * HF_PLANE + p * 16) = o;
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+          const int t = t0 + u * HF_PRODUCERS;
+          if (t >= HF_PIX * NCH) break;
+          const int p = t / NCH, kc = t - p * NCH;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (in[u]) {
+            const T* ea = reinterpret_cast<const T*>(&va[u]);
+            const T* eb = reinterpret_cast<const T*>(&vb[u]);
+            const T* ec = reinterpret_cast<const T*>(&vc[u]);
+            const T* ed = reinterpret_cast<const T*>(&vd[u]);
+            float v[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              v[jj] = (1.f - ly[u]) * ((1.f - lx[u]) * to_f<T>(ea[jj]) + lx[u] * to_f<T>(eb[jj])) +
+                      ly[u] * ((1.f - lx[u]) * to_f<T>(ec[jj]) + lx[u] * to_f<T>(ed[jj]));
+            o.x = pack2(from_f<T>(v[0]), from_f<T>(v[1]));
+            o.y = pack2(from_f<T>(v[2]), from_f<T>(v[3]));
+            o.z = pack2(from_f<T>(v[4]), from_f<T>(v[5]));
+            o.w = pack2(from_f<T>(v[6]), from_f<T>(v[7]));
+          }
+          *reinterpret_cast<uint4*>(hb + (size_t)kc * HF_PLANE + p * 16) = o;
+        }
       }
       fence_proxy_async();
       mbar_arrive(&halo_full[b]);
@@ -127,10 +154,11 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t b = it & 1, ph = (it >> 1) & 1;
+        const uint32_t hs = it % HF_STAGES;
         mbar_wait(&acc_empty[b], ph ^ 1);
-        mbar_wait(&halo_full[b], ph);
+        mbar_wait(&halo_full[hs], (it / HF_STAGES) & 1);
         fence_after_sync();
-        const uint32_t ha = smem_u32(halo + b * HALO_BYTES);
+        const uint32_t ha = smem_u32(halo + hs * HALO_BYTES);
         const uint32_t wa = smem_u32(wsm);
         uint32_t first = 1;
 #pragma unroll
@@ -144,7 +172,7 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
             first = 0;
           }
         }
-        mma_commit(&halo_empty[b]);
+        mma_commit(&halo_empty[hs]);
         mma_commit(&acc_full[b]);
       }
     }

@@ -348,19 +348,26 @@ inline void head_fused(Launch& L, int dtype, const void* x, const void* w, const
 template <typename T, int HD>
 void launch_temporal(Launch& L, const void* qkv, void* out, int B, int Tn, int hw, int C) {
   const int heads = 8;
-  int hpb = heads;
-  auto smem_for = [&](int h) { return (size_t)Tn * (3 * h * HD + 1) * sizeof(float); };
-  while (hpb > 1 && smem_for(hpb) > 100 * 1024) hpb >>= 1;
-  const size_t smem = smem_for(hpb);
+  // shared memory per (position, head): K and V in fp32, q/o in T
+  const size_t per = (size_t)Tn * HD * (8 + sizeof(T));
+  int hg = heads;
+  while (hg > 1 && hg * per > 64 * 1024) hg >>= 1;
+  int pb = (int)((64 * 1024) / (hg * per));
+  if (pb < 1) pb = 1;
+  if (pb > 4) pb = 4;
+  while (pb > 1 && 32 * hg * pb > ta_max_threads<HD>()) --pb;
+  while (hg > 1 && 32 * hg * pb > ta_max_threads<HD>()) hg >>= 1;
+  if (pb > hw) pb = hw;
+  const size_t smem = (size_t)pb * hg * per + (size_t)Tn * 16 + 16;
   auto kern = temporal_attention_kernel<T, HD>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  dim3 grid(hw, B, heads / hpb);
+  dim3 grid((hw + pb - 1) / pb, B, heads / hg);
   L.note(4.0 * B * hw * heads * (double)Tn * Tn * HD, 4.0 * B * Tn * hw * C * sizeof(T));
-  kern<<<grid, 32 * hpb, smem, L.stream>>>((const T*)qkv, (T*)out, Tn, hw, C, hpb);
+  kern<<<grid, 32 * hg * pb, smem, L.stream>>>((const T*)qkv, (T*)out, Tn, hw, C, pb, hg);
   L.check("temporal_attention");
 }
 
