@@ -3,7 +3,7 @@
 //   C[M,N] = A[M,K] * W[N,K]^T   (16-bit operands, fp32 accumulation in TMEM)
 //
 // One CTA per SM loops over 128 x BN output tiles (static round-robin, n fastest so that CTAs
-// running together share A tiles through L2).  384 threads:
+// running together share A tiles through L2).  640 threads:
 //   warp 0       TMA producer  -- cp.async.bulk.tensor loads of the A and W k-blocks into a ring
 //                of 128B(64B)-swizzled shared-memory stages, completion on mbarriers; the ring
 //                runs ahead across tile boundaries
@@ -11,8 +11,8 @@
 //                into one of TWO accumulator buffers in TMEM; tcgen05.commit releases the smem
 //                stage / hands the finished accumulator to its epilogue warpgroup
 //   warps 2,3    idle (keep the epilogue warpgroups 4-warp aligned for the TMEM lane quarters)
-//   warps 4..7   epilogue warpgroup 0: accumulator buffer 0 (even tiles of this CTA)
-//   warps 8..11  epilogue warpgroup 1: accumulator buffer 1 (odd tiles)
+//   warps 4..19  four epilogue warpgroups: warpgroup wg drains columns [half*BN/2, +BN/2) of
+//                accumulator buffer (wg & 1) (even / odd tiles of this CTA), half = wg >> 1
 //                tcgen05.ld (lane = row), fused bias / row-bias / GELU / GEGLU / residual / ReLU /
 //                pixel-shuffle / disparity-head epilogue (common.cuh), 16-byte vector stores.
 // So the epilogue of tile i overlaps the mainloop of tile i+1 -- with K = 384 (ViT-S) the
@@ -36,7 +36,7 @@ struct ConvTile {
 };
 
 constexpr int GT_BM = 128;
-constexpr int GT_THREADS = 384;
+constexpr int GT_THREADS = 640;
 
 template <int BN, int BK> constexpr int gt_stage_bytes() { return (GT_BM + BN) * BK * 2; }
 template <int BN> constexpr uint32_t gt_tmem_cols() { return 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512; }
@@ -63,31 +63,31 @@ template <typename T> __device__ __forceinline__ float4 ld4_as_f32(const void* p
   return make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// The fused epilogue on 8 row segments (4 consecutive columns starting at n of rows mm[it] ->
+// The fused epilogue on NS row segments (4 consecutive columns starting at n of rows mm[it] ->
 // output rows oo[it], oo < 0 = masked).  Same order of operations as epi_apply (common.cuh):
 // bias, per-frame row bias, GELU, residual(s), ReLU / sigmoid, stores.  Every stage is a loop over
-// the 8 segments so the runtime switches cost one branch per stage and the loads of a stage are
+// the NS segments so the runtime switches cost one branch per stage and the loads of a stage are
 // all in flight together.
-template <typename T>
-__device__ __forceinline__ void gt_apply8(const Epi& e, float4* a, const int* mm, const int* oo, int n) {
+template <typename T, int NS>
+__device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm, const int* oo, int n) {
   if (e.bias) {
     const float4 b = *reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) f4_add(a[it], b);
+    for (int it = 0; it < NS; ++it) f4_add(a[it], b);
   }
   if (e.rowbias) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it)
+    for (int it = 0; it < NS; ++it)
       if (oo[it] >= 0) f4_add(a[it], *reinterpret_cast<const float4*>(e.rowbias + (long long)((mm[it] / e.rb_div) % e.rb_mod) * e.rb_ld + n));
   }
   if (e.act == ACT_GELU) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < NS; ++it) {
       a[it].x = gelu_act<T>(a[it].x); a[it].y = gelu_act<T>(a[it].y);
       a[it].z = gelu_act<T>(a[it].z); a[it].w = gelu_act<T>(a[it].w);
     }
   }
-  long long orow[8];
+  long long orow[NS];
   int ocol = n;
   if (e.map == MAP_PIXSHUF) {
     // m = (f, y, x) over the ps_h x ps_w grid; n = (ky*k + kx)*ps_c + c
@@ -96,7 +96,7 @@ __device__ __forceinline__ void gt_apply8(const Epi& e, float4* a, const int* mm
     const int ky = tap / e.ps_k, kx = tap - ky * e.ps_k;
     const int hw = e.ps_h * e.ps_w;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < NS; ++it) {
       const int f = mm[it] / hw;
       const int r = mm[it] - f * hw;
       const int y = r / e.ps_w, x = r - y * e.ps_w;
@@ -104,28 +104,28 @@ __device__ __forceinline__ void gt_apply8(const Epi& e, float4* a, const int* mm
     }
   } else {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) orow[it] = oo[it];
+    for (int it = 0; it < NS; ++it) orow[it] = oo[it];
   }
   if (e.res1) {
-    float4 r[8];
+    float4 r[NS];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res1, e.res1_f32, orow[it] * e.ld_res1 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < NS; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res1, e.res1_f32, orow[it] * e.ld_res1 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) f4_add(a[it], r[it]);
+    for (int it = 0; it < NS; ++it) f4_add(a[it], r[it]);
   }
   if (e.res2) {
-    float4 r[8];
+    float4 r[NS];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res2, e.res2_f32, orow[it] * e.ld_res2 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < NS; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res2, e.res2_f32, orow[it] * e.ld_res2 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) f4_add(a[it], r[it]);
+    for (int it = 0; it < NS; ++it) f4_add(a[it], r[it]);
   }
   if (e.act == ACT_RELU) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) { a[it].x = fmaxf(a[it].x, 0.f); a[it].y = fmaxf(a[it].y, 0.f); a[it].z = fmaxf(a[it].z, 0.f); a[it].w = fmaxf(a[it].w, 0.f); }
+    for (int it = 0; it < NS; ++it) { a[it].x = fmaxf(a[it].x, 0.f); a[it].y = fmaxf(a[it].y, 0.f); a[it].z = fmaxf(a[it].z, 0.f); a[it].w = fmaxf(a[it].w, 0.f); }
   } else if (e.act == ACT_SIGMOID) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < NS; ++it) {
       a[it].x = 1.f / (1.f + __expf(-e.sig_sign * a[it].x)); a[it].y = 1.f / (1.f + __expf(-e.sig_sign * a[it].y));
       a[it].z = 1.f / (1.f + __expf(-e.sig_sign * a[it].z)); a[it].w = 1.f / (1.f + __expf(-e.sig_sign * a[it].w));
     }
@@ -133,11 +133,11 @@ __device__ __forceinline__ void gt_apply8(const Epi& e, float4* a, const int* mm
   if (e.out) {
     if (e.out_f32) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it)
+      for (int it = 0; it < NS; ++it)
         if (oo[it] >= 0) *reinterpret_cast<float4*>((float*)e.out + orow[it] * e.ldo + ocol) = a[it];
     } else {
 #pragma unroll
-      for (int it = 0; it < 8; ++it)
+      for (int it = 0; it < NS; ++it)
         if (oo[it] >= 0) {
           uint2 w;
           w.x = pack2(from_f<T>(a[it].x), from_f<T>(a[it].y));
@@ -148,7 +148,7 @@ __device__ __forceinline__ void gt_apply8(const Epi& e, float4* a, const int* mm
   }
   if (e.out_relu) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it)
+    for (int it = 0; it < NS; ++it)
       if (oo[it] >= 0) {
         uint2 w;
         w.x = pack2(from_f<T>(fmaxf(a[it].x, 0.f)), from_f<T>(fmaxf(a[it].y, 0.f)));
@@ -165,12 +165,15 @@ __device__ __forceinline__ void gt_apply8(const Epi& e, float4* a, const int* mm
 // columns of one row (128-bit accesses, 4 full rows per instruction).
 template <typename T, int BN>
 __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool valid, long long m, long long orow_lin,
-                                            int n0, int tile_n, uint32_t* stg, int lane) {
+                                            int n0, int tile_n, uint32_t* stg, int lane, int half) {
   const int m32 = (int)m;                          // rows < 2^31 (checked by the launcher)
   const int o32 = valid ? (int)orow_lin : -1;
   const int j = lane & 7, rsub = lane >> 3;
+  // the two warpgroups of an accumulator split its columns: [0, BN/2) and [BN/2, BN)
+  constexpr int CH0 = (BN >= 64) ? BN / 2 : BN;
   if (e.act == ACT_HEAD) {
     // whole row in one tile (BN == N == 32): relu(conv+b) . w + b -> relu  (dpt.py:118-123)
+    if (half != 0) return;
     if constexpr (BN == 32) {
       float v[32];
       tmem_ld32(trow, v);
@@ -186,8 +189,8 @@ __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool va
   } else if (e.act == ACT_GEGLU) {
     // BN == 128: columns [0,64) value, [64,128) gate (pack.py pairs them per tile)
     if constexpr (BN == 128) {
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
+      {
+        const int c = half * 32;
         float v[32];
         float4 hv[8];
         tmem_ld32(trow + c, v);
@@ -219,22 +222,26 @@ __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool va
       }
     }
   } else {
+    if (BN < 64 && half != 0) return;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = half * CH0; c < (BN >= 64 ? (half + 1) * CH0 : BN); c += 32) {
       float v[32];
       tmem_ld32(trow + c, v);
       gt_stage_write(stg, lane, v);
       __syncwarp();
-      float4 a[8];
-      int mm[8], oo[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + rsub;
-        mm[it] = __shfl_sync(0xffffffffu, m32, rr);
-        oo[it] = __shfl_sync(0xffffffffu, o32, rr);
-        a[it] = gt_stage_read(stg, rr, j);
+      for (int hb = 0; hb < 2; ++hb) {   // 2 x 4 row segments: keeps the epilogue under 96 registers
+        float4 a[4];
+        int mm[4], oo[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = (hb * 4 + it) * 4 + rsub;
+          mm[it] = __shfl_sync(0xffffffffu, m32, rr);
+          oo[it] = __shfl_sync(0xffffffffu, o32, rr);
+          a[it] = gt_stage_read(stg, rr, j);
+        }
+        gt_applyN<T, 4>(e, a, mm, oo, n0 + c + 4 * j);
       }
-      gt_apply8<T>(e, a, mm, oo, n0 + c + 4 * j);
       __syncwarp();
     }
   }
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint64_t* tfull_bar = empty_bar + stages;   // 2: accumulator buffer b complete
   uint64_t* tempty_bar = tfull_bar + 2;       // 2: accumulator buffer b drained by its epilogue warpgroup
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint32_t* stg_base = tmem_slot + 4;          // 8 warps x GT_STG_WORDS
+  uint32_t* stg_base = tmem_slot + 4;          // 16 warps x GT_STG_WORDS
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = K / BK;
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], 256);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -345,8 +352,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // epilogue warpgroup g drains accumulator buffer g; warp w may touch TMEM lanes [32*(w%4), +32)
-    const uint32_t g = (warp - 4) >> 2;
+    // epilogue warpgroups 0..3: accumulator buffer g = wg & 1, column half = wg >> 1;
+    // warp w may touch TMEM lanes [32*(w%4), +32)
+    const uint32_t wg = (warp - 4) >> 2;
+    const uint32_t g = wg & 1;
+    const int half = wg >> 1;
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row inside the tile
     uint32_t it = 0;
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       mbar_wait(&tfull_bar[g], (it >> 1) & 1);
       fence_after_sync();
       gt_epilogue<T, BN>(e, tmem_base + ((uint32_t)(q * 32) << 16) + g * BN, valid, m, orow, tile_n * BN, tile_n,
-                         stg_base + (warp - 4) * GT_STG_WORDS, lane);
+                         stg_base + (warp - 4) * GT_STG_WORDS, lane, half);
       fence_before_sync();
       mbar_arrive(&tempty_bar[g]);
     }

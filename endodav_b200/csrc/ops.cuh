@@ -172,7 +172,7 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
   }
   const int kblocks = a.K / BK;
   const int stage_bytes = gt_stage_bytes<BN, BK>();
-  const size_t stg_bytes = 8 * (size_t)GT_STG_WORDS * 4;   // epilogue transposition buffers
+  const size_t stg_bytes = 16 * (size_t)GT_STG_WORDS * 4;   // epilogue transposition buffers
   int stages = (int)((220 * 1024 - stg_bytes - 2048) / stage_bytes);  // one persistent CTA per SM owns the shared memory
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
