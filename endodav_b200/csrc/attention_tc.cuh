@@ -211,9 +211,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           for (int i = 0; i < 128; ++i)
             if (i >= valid) sv[i] = 0xff800000u;  // -inf
         }
-        float mx = __uint_as_float(sv[0]);
+        // 8 independent partial maxima (a single running max would be a 127-deep dependent chain)
+        float pm[8];
 #pragma unroll
-        for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < 8; ++i) pm[i] = __uint_as_float(sv[i]);
+#pragma unroll
+        for (int i = 8; i < 128; ++i) pm[i & 7] = fmaxf(pm[i & 7], __uint_as_float(sv[i]));
+        const float mx = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
         // lazy rescale: keep the old reference max unless the row max grew by more than 2^8
         float factor = 1.f;
         const bool grow = mx > m_used + 8.f / LOG2E;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           }
         }
         const float neg = -m_used * LOG2E;
-        float lsum = 0.f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial row sums
 #pragma unroll
         for (int c = 0; c < 128; c += 64) {
           uint32_t pv[32];
@@ -243,12 +247,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           for (int i = 0; i < 32; ++i) {
             const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c + 2 * i]), LOG2E, neg));
             const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 2 * i + 1]), LOG2E, neg));
-            lsum += p0 + p1;
+            ls[i & 3] += p0 + p1;
             pv[i] = pack_pair(p0, p1, T());
           }
           tmem_st32(tP + c / 2, pv);
         }
-        l += lsum;
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         tmem_st_wait();
         fence_before_sync();
         mbar_arrive(&p_full[t]);

@@ -32,6 +32,40 @@ template <int CIN> constexpr size_t hf_smem_bytes() {
   return 1024 + (size_t)9 * (CIN / 8) * 512 + hf_stages<CIN>() * (size_t)(CIN / 8) * HF_PLANE + 256;
 }
 
+// w00*a + w01*b + w10*c + w11*d on 8 packed 16-bit channels, in packed 16-bit arithmetic
+// (1 HMUL2 + 3 HFMA2 per pair; no fp32 round trip: the producers are instruction-bound)
+__device__ __forceinline__ uint4 hf_lerp4(const uint4& a, const uint4& b, const uint4& c, const uint4& d, float w00,
+                                          float w01, float w10, float w11, f16) {
+  const __half2 h00 = __float2half2_rn(w00), h01 = __float2half2_rn(w01), h10 = __float2half2_rn(w10), h11 = __float2half2_rn(w11);
+  uint4 o;
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+  const __half2* pc = reinterpret_cast<const __half2*>(&c);
+  const __half2* pd = reinterpret_cast<const __half2*>(&d);
+  __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) po[i] = __hfma2(h11, pd[i], __hfma2(h10, pc[i], __hfma2(h01, pb[i], __hmul2(h00, pa[i]))));
+  return o;
+}
+__device__ __forceinline__ uint4 hf_lerp4(const uint4& a, const uint4& b, const uint4& c, const uint4& d, float w00,
+                                          float w01, float w10, float w11, bf16) {
+  // bf16 has too few mantissa bits for packed accumulation: fp32 lerp, one rounding
+  const bf16* ea = reinterpret_cast<const bf16*>(&a);
+  const bf16* eb = reinterpret_cast<const bf16*>(&b);
+  const bf16* ec = reinterpret_cast<const bf16*>(&c);
+  const bf16* ed = reinterpret_cast<const bf16*>(&d);
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    v[i] = w00 * to_f<bf16>(ea[i]) + w01 * to_f<bf16>(eb[i]) + w10 * to_f<bf16>(ec[i]) + w11 * to_f<bf16>(ed[i]);
+  uint4 o;
+  o.x = pack2(from_f<bf16>(v[0]), from_f<bf16>(v[1]));
+  o.y = pack2(from_f<bf16>(v[2]), from_f<bf16>(v[3]));
+  o.z = pack2(from_f<bf16>(v[4]), from_f<bf16>(v[5]));
+  o.w = pack2(from_f<bf16>(v[6]), from_f<bf16>(v[7]));
+  return o;
+}
+
 template <typename T, int CIN>
 __global__ void __launch_bounds__(HF_THREADS, 1)
     head_fused_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
@@ -85,6 +119,9 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
     const int pt = threadIdx.x - 5 * 32;
     const float sy = (OH > 1) ? (float)(H1 - 1) / (float)(OH - 1) : 0.f;
     const float sx = (OW > 1) ? (float)(W1 - 1) / (float)(OW - 1) : 0.f;
+    // the (halo pixel, channel chunk) tasks of this thread are the same for every tile
+    constexpr int NT = (HF_PIX * NCH + HF_PRODUCERS - 1) / HF_PRODUCERS;
+    static_assert(NT <= 12, "too many tasks per producer thread");
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t b = it % HF_STAGES;
@@ -95,54 +132,41 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
       mbar_wait(&halo_empty[b], ((it / HF_STAGES) & 1) ^ 1);
       unsigned char* hb = halo + b * HALO_BYTES;
       const T* xf = x + (size_t)f * H1 * W1 * CIN;
-      constexpr int NT = 3;   // tasks per batch: all 12 loads are issued before the first use
-      for (int t0 = pt; t0 < HF_PIX * NCH; t0 += NT * HF_PRODUCERS) {
-        uint4 va[NT], vb[NT], vc[NT], vd[NT];
-        float ly[NT], lx[NT];
-        bool in[NT];
+      constexpr int NB = NT < 3 ? NT : 3;   // tasks per batch: all 4*NB loads are issued before the first use
+#pragma unroll 1
+      for (int u0 = 0; u0 < NT; u0 += NB) {
+        uint4 va[NB], vb[NB], vc[NB], vd[NB];
+        float w00[NB], w01[NB], w10[NB], w11[NB];
+        int dst[NB];
 #pragma unroll
-        for (int u = 0; u < NT; ++u) {
-          const int t = t0 + u * HF_PRODUCERS;
+        for (int u = 0; u < NB; ++u) {
+          const int t = pt + (u0 + u) * HF_PRODUCERS;
           const int p = t / NCH, kc = t - p * NCH;
           const int hy = p / HF_HW, hx = p - hy * HF_HW;
           const int oy = y0t + hy, ox = x0t + hx;
-          in[u] = (t < HF_PIX * NCH) && oy >= 0 && oy < OH && ox >= 0 && ox < OW;
-          // identical arithmetic to upsample_nhwc_kernel (elementwise.cuh)
+          dst[u] = (t < HF_PIX * NCH) ? kc * HF_PLANE + p * 16 : -1;
+          const bool in = dst[u] >= 0 && oy >= 0 && oy < OH && ox >= 0 && ox < OW;
+          // source coordinates exactly as upsample_nhwc_kernel / ATen (align_corners=True, float32)
           const float fy = sy * oy, fx = sx * ox;
           const int ya = (int)fy, xa = (int)fx;
-          const int yb = min(ya + 1, H1 - 1), xb = min(xa + 1, W1 - 1);
-          ly[u] = fy - ya;
-          lx[u] = fx - xa;
-          if (in[u]) {
-            va[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)ya * W1 + xa) * CIN + kc * 8);
-            vb[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)ya * W1 + xb) * CIN + kc * 8);
-            vc[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)yb * W1 + xa) * CIN + kc * 8);
-            vd[u] = *reinterpret_cast<const uint4*>(xf + ((size_t)yb * W1 + xb) * CIN + kc * 8);
+          const float ly = fy - ya, lx = fx - xa;
+          w00[u] = in ? (1.f - ly) * (1.f - lx) : 0.f;
+          w01[u] = in ? (1.f - ly) * lx : 0.f;
+          w10[u] = in ? ly * (1.f - lx) : 0.f;
+          w11[u] = in ? ly * lx : 0.f;
+          const int yc = min(max(ya, 0), H1 - 1), xc = min(max(xa, 0), W1 - 1);   // clamped: loads stay in bounds, weights are 0 outside
+          const int dxo = (xc + 1 < W1) ? CIN : 0, dyo = (yc + 1 < H1) ? W1 * CIN : 0;
+          const T* s0 = xf + ((size_t)yc * W1 + xc) * CIN + kc * 8;
+          if (dst[u] >= 0) {
+            va[u] = *reinterpret_cast<const uint4*>(s0);
+            vb[u] = *reinterpret_cast<const uint4*>(s0 + dxo);
+            vc[u] = *reinterpret_cast<const uint4*>(s0 + dyo);
+            vd[u] = *reinterpret_cast<const uint4*>(s0 + dyo + dxo);
           }
         }
 #pragma unroll
-        for (int u = 0; u < NT; ++u) {
-          const int t = t0 + u * HF_PRODUCERS;
-          if (t >= HF_PIX * NCH) break;
-          const int p = t / NCH, kc = t - p * NCH;
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if (in[u]) {
-            const T* ea = reinterpret_cast<const T*>(&va[u]);
-            const T* eb = reinterpret_cast<const T*>(&vb[u]);
-            const T* ec = reinterpret_cast<const T*>(&vc[u]);
-            const T* ed = reinterpret_cast<const T*>(&vd[u]);
-            float v[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              v[jj] = (1.f - ly[u]) * ((1.f - lx[u]) * to_f<T>(ea[jj]) + lx[u] * to_f<T>(eb[jj])) +
-                      ly[u] * ((1.f - lx[u]) * to_f<T>(ec[jj]) + lx[u] * to_f<T>(ed[jj]));
-            o.x = pack2(from_f<T>(v[0]), from_f<T>(v[1]));
-            o.y = pack2(from_f<T>(v[2]), from_f<T>(v[3]));
-            o.z = pack2(from_f<T>(v[4]), from_f<T>(v[5]));
-            o.w = pack2(from_f<T>(v[6]), from_f<T>(v[7]));
-          }
-          *reinterpret_cast<uint4*>(hb + (size_t)kc * HF_PLANE + p * 16) = o;
-        }
+        for (int u = 0; u < NB; ++u)
+          if (dst[u] >= 0) *reinterpret_cast<uint4*>(hb + dst[u]) = hf_lerp4(va[u], vb[u], vc[u], vd[u], w00[u], w01[u], w10[u], w11[u], T());
       }
       fence_proxy_async();
       mbar_arrive(&halo_full[b]);

@@ -16,7 +16,7 @@ def rnd(*s, scale=1.0):
     return (torch.randn(*s, generator=g) * scale).to(dt).cuda()
 
 
-which = sys.argv[1:] or ["fc1", "qkv", "fc2", "attn", "rcu", "tattn"]
+which = sys.argv[1:] or ["fc1", "qkv", "fc2", "attn", "rcu", "tattn", "head"]
 reps = 2
 for w in which:
     for _ in range(reps):
@@ -30,6 +30,9 @@ for w in which:
             eng.op_attention(rnd(M, 1152, scale=0.5), 32, 1370, 6)
         elif w == "rcu":
             eng.op_conv3x3(rnd(32, 148, 148, 64), rnd(64, 576, scale=0.04), torch.zeros(64).cuda(), True)
+        elif w == "head":
+            eng.op_disp_head(rnd(32, 296, 296, 32), rnd(32, 288, scale=0.06), torch.zeros(32).cuda(),
+                             torch.ones(33).cuda() * 0.1, 518, 518)
         elif w == "tattn":
             eng.op_temporal_attention(rnd(32 * 5476, 192, scale=0.7), 1, 32, 5476, 64)
     torch.cuda.synchronize()
