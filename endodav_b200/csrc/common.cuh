@@ -162,6 +162,7 @@ struct Epi {
   int ps_k, ps_h, ps_w, ps_c;  // MAP_PIXSHUF: k, grid h, grid w, channels per tap (padded)
   float head_b;
   float sig_sign;  // ACT_SIGMOID: sigmoid(sig_sign * x)
+  int kind;        // tcgen05 epilogue specialisation (gemm_tc.cuh EF_* mask) or -1: set by the launcher
 };
 
 // maps GEMM row m -> output row for the column-independent mappings

@@ -63,24 +63,45 @@ template <typename T> __device__ __forceinline__ float4 ld4_as_f32(const void* p
   return make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// Compile-time epilogue kinds.  The runtime-flag version of this code is a chain of
+// `if (flag) { unrolled block }`: every skipped block is a taken branch to a far target, and with
+// the epilogue far larger than the L0 instruction cache each of them is an instruction-fetch stall
+// (ncu: stall_no_inst on every other line, ~2 500 cycles per 32-column chunk).  The hot call sites
+// of the forward therefore get straight-line instantiations (F >= 0: bit mask below); anything
+// else (row-bias tables, pixel shuffle, sigmoid) runs the generic F = -1 version.
+enum { EF_BIAS = 1, EF_GELU = 2, EF_RELU = 4, EF_RES1_F32 = 8, EF_RES1_T = 16, EF_RES2_T = 32, EF_OUT_F32 = 64, EF_OUT_RELU = 128 };
+
 // The fused epilogue on NS row segments (4 consecutive columns starting at n of rows mm[it] ->
 // output rows oo[it], oo < 0 = masked).  Same order of operations as epi_apply (common.cuh):
 // bias, per-frame row bias, GELU, residual(s), ReLU / sigmoid, stores.  Every stage is a loop over
-// the NS segments so the runtime switches cost one branch per stage and the loads of a stage are
-// all in flight together.
-template <typename T, int NS>
-__device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm, const int* oo, int n) {
-  if (e.bias) {
-    const float4 b = *reinterpret_cast<const float4*>(e.bias + n);
+// the NS segments so the loads of a stage are all in flight together.
+template <typename T, int NS, int F>
+__device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm, const int* oo, int n,
+                                          const float* bias4) {
+  constexpr bool S = F >= 0;
+  const bool has_bias = S ? ((F & EF_BIAS) != 0) : (bias4 != nullptr);
+  const bool do_gelu = S ? ((F & EF_GELU) != 0) : (e.act == ACT_GELU);
+  const bool do_relu = S ? ((F & EF_RELU) != 0) : (e.act == ACT_RELU);
+  const bool has_res1 = S ? ((F & (EF_RES1_F32 | EF_RES1_T)) != 0) : (e.res1 != nullptr);
+  const int res1_f32 = S ? ((F & EF_RES1_F32) != 0) : e.res1_f32;
+  const bool has_res2 = S ? ((F & EF_RES2_T) != 0) : (e.res2 != nullptr);
+  const int res2_f32 = S ? 0 : e.res2_f32;
+  const bool has_out = S ? true : (e.out != nullptr);
+  const int out_f32 = S ? ((F & EF_OUT_F32) != 0) : e.out_f32;
+  const bool has_out_relu = S ? ((F & EF_OUT_RELU) != 0) : (e.out_relu != nullptr);
+  if (has_bias) {
+    // the bias slice was staged in shared memory before the accumulator wait (with ~200 KB of the
+    // SM's memory carved out as shared, L1 holds almost nothing)
+    const float4 b = *reinterpret_cast<const float4*>(bias4);
 #pragma unroll
     for (int it = 0; it < NS; ++it) f4_add(a[it], b);
   }
-  if (e.rowbias) {
+  if (!S && e.rowbias) {
 #pragma unroll
     for (int it = 0; it < NS; ++it)
       if (oo[it] >= 0) f4_add(a[it], *reinterpret_cast<const float4*>(e.rowbias + (long long)((mm[it] / e.rb_div) % e.rb_mod) * e.rb_ld + n));
   }
-  if (e.act == ACT_GELU) {
+  if (do_gelu) {
 #pragma unroll
     for (int it = 0; it < NS; ++it) {
       a[it].x = gelu_act<T>(a[it].x); a[it].y = gelu_act<T>(a[it].y);
@@ -89,7 +110,7 @@ __device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm
   }
   long long orow[NS];
   int ocol = n;
-  if (e.map == MAP_PIXSHUF) {
+  if (!S && e.map == MAP_PIXSHUF) {
     // m = (f, y, x) over the ps_h x ps_w grid; n = (ky*k + kx)*ps_c + c
     const int tap = n / e.ps_c;
     ocol = n - tap * e.ps_c;
@@ -106,32 +127,32 @@ __device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm
 #pragma unroll
     for (int it = 0; it < NS; ++it) orow[it] = oo[it];
   }
-  if (e.res1) {
+  if (has_res1) {
     float4 r[NS];
 #pragma unroll
-    for (int it = 0; it < NS; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res1, e.res1_f32, orow[it] * e.ld_res1 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < NS; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res1, res1_f32, orow[it] * e.ld_res1 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < NS; ++it) f4_add(a[it], r[it]);
   }
-  if (e.res2) {
+  if (has_res2) {
     float4 r[NS];
 #pragma unroll
-    for (int it = 0; it < NS; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res2, e.res2_f32, orow[it] * e.ld_res2 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < NS; ++it) r[it] = (oo[it] >= 0) ? ld4_as_f32<T>(e.res2, res2_f32, orow[it] * e.ld_res2 + ocol) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < NS; ++it) f4_add(a[it], r[it]);
   }
-  if (e.act == ACT_RELU) {
+  if (do_relu) {
 #pragma unroll
     for (int it = 0; it < NS; ++it) { a[it].x = fmaxf(a[it].x, 0.f); a[it].y = fmaxf(a[it].y, 0.f); a[it].z = fmaxf(a[it].z, 0.f); a[it].w = fmaxf(a[it].w, 0.f); }
-  } else if (e.act == ACT_SIGMOID) {
+  } else if (!S && e.act == ACT_SIGMOID) {
 #pragma unroll
     for (int it = 0; it < NS; ++it) {
       a[it].x = 1.f / (1.f + __expf(-e.sig_sign * a[it].x)); a[it].y = 1.f / (1.f + __expf(-e.sig_sign * a[it].y));
       a[it].z = 1.f / (1.f + __expf(-e.sig_sign * a[it].z)); a[it].w = 1.f / (1.f + __expf(-e.sig_sign * a[it].w));
     }
   }
-  if (e.out) {
-    if (e.out_f32) {
+  if (has_out) {
+    if (out_f32) {
 #pragma unroll
       for (int it = 0; it < NS; ++it)
         if (oo[it] >= 0) *reinterpret_cast<float4*>((float*)e.out + orow[it] * e.ldo + ocol) = a[it];
@@ -146,7 +167,7 @@ __device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm
         }
     }
   }
-  if (e.out_relu) {
+  if (has_out_relu) {
 #pragma unroll
     for (int it = 0; it < NS; ++it)
       if (oo[it] >= 0) {
@@ -158,6 +179,35 @@ __device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm
   }
 }
 
+// The row-segment path of gt_epilogue for columns [half*BN/2, +BN/2) of one accumulator.
+template <typename T, int BN, int F>
+__device__ __forceinline__ void gt_epi_rows(const Epi& e, uint32_t trow, int m32, int o32, int n0, uint32_t* stg, int lane,
+                                            int half, const float* bias_s) {
+  constexpr int CH0 = (BN >= 64) ? BN / 2 : BN;
+  const int j = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+  for (int c = half * CH0; c < (BN >= 64 ? (half + 1) * CH0 : BN); c += 32) {
+    float v[32];
+    tmem_ld32(trow + c, v);
+    gt_stage_write(stg, lane, v);
+    __syncwarp();
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {   // 2 x 4 row segments: keeps the epilogue under 96 registers
+      float4 a[4];
+      int mm[4], oo[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = (hb * 4 + it) * 4 + rsub;
+        mm[it] = __shfl_sync(0xffffffffu, m32, rr);
+        oo[it] = __shfl_sync(0xffffffffu, o32, rr);
+        a[it] = gt_stage_read(stg, rr, j);
+      }
+      gt_applyN<T, 4, F>(e, a, mm, oo, n0 + c + 4 * j, bias_s ? bias_s + (c - half * CH0) + 4 * j : nullptr);
+    }
+    __syncwarp();
+  }
+}
+
 // epilogue of one 128 x BN accumulator: thread = row `r` of the tile, TMEM address `trow`.
 // The accumulator leaves TMEM in the row-owner domain (tcgen05.ld: lane = row) and is transposed
 // per warp through `stg`, so that the fused epilogue math (common.cuh: epi_apply) and every
@@ -165,7 +215,8 @@ __device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm
 // columns of one row (128-bit accesses, 4 full rows per instruction).
 template <typename T, int BN>
 __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool valid, long long m, long long orow_lin,
-                                            int n0, int tile_n, uint32_t* stg, int lane, int half) {
+                                            int n0, int tile_n, uint32_t* stg, int lane, int half,
+                                            const float* bias_s) {
   const int m32 = (int)m;                          // rows < 2^31 (checked by the launcher)
   const int o32 = valid ? (int)orow_lin : -1;
   const int j = lane & 7, rsub = lane >> 3;
@@ -223,26 +274,21 @@ __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool va
     }
   } else {
     if (BN < 64 && half != 0) return;
-#pragma unroll 1
-    for (int c = half * CH0; c < (BN >= 64 ? (half + 1) * CH0 : BN); c += 32) {
-      float v[32];
-      tmem_ld32(trow + c, v);
-      gt_stage_write(stg, lane, v);
-      __syncwarp();
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {   // 2 x 4 row segments: keeps the epilogue under 96 registers
-        float4 a[4];
-        int mm[4], oo[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr = (hb * 4 + it) * 4 + rsub;
-          mm[it] = __shfl_sync(0xffffffffu, m32, rr);
-          oo[it] = __shfl_sync(0xffffffffu, o32, rr);
-          a[it] = gt_stage_read(stg, rr, j);
-        }
-        gt_applyN<T, 4>(e, a, mm, oo, n0 + c + 4 * j);
-      }
-      __syncwarp();
+    switch (e.kind) {
+#define EDV_EPI_CASE(F_) case F_: gt_epi_rows<T, BN, F_>(e, trow, m32, o32, n0, stg, lane, half, bias_s); break;
+      EDV_EPI_CASE(EF_BIAS)                                              // qkv, projects, out_conv, output_conv1
+      EDV_EPI_CASE(EF_BIAS | EF_GELU)                                    // fc1
+      EDV_EPI_CASE(EF_BIAS | EF_RES1_F32 | EF_OUT_F32)                   // attn.proj, fc2, temporal to_out: x += ...
+      EDV_EPI_CASE(EF_BIAS | EF_OUT_F32)                                 // temporal proj_in
+      EDV_EPI_CASE(EF_BIAS | EF_RES1_F32)                                // temporal ff.net.2
+      EDV_EPI_CASE(EF_BIAS | EF_RES1_T)                                  // temporal proj_out, RCU conv2
+      EDV_EPI_CASE(EF_BIAS | EF_RES1_T | EF_OUT_RELU)
+      EDV_EPI_CASE(EF_BIAS | EF_RES1_T | EF_RES2_T)
+      EDV_EPI_CASE(EF_BIAS | EF_RES1_T | EF_RES2_T | EF_OUT_RELU)
+      EDV_EPI_CASE(EF_BIAS | EF_RELU)                                    // RCU conv1
+      EDV_EPI_CASE(EF_OUT_RELU)                                          // layer*_rn
+#undef EDV_EPI_CASE
+      default: gt_epi_rows<T, BN, -1>(e, trow, m32, o32, n0, stg, lane, half, bias_s); break;
     }
   }
 }
@@ -269,6 +315,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;       // 2: accumulator buffer b drained by its epilogue warpgroup
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint32_t* stg_base = tmem_slot + 4;          // 16 warps x GT_STG_WORDS
+  float* bias_base = reinterpret_cast<float*>(stg_base + 16 * GT_STG_WORDS);   // 16 warps x 128 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = K / BK;
@@ -380,10 +427,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         valid = m < M;
         orow = epi_row(e, m);
       }
+      // stage this warp's bias slice (columns [half*BN/2, +BN/2) of the tile) while the mainloop runs
+      float* bias_s = nullptr;
+      if (e.bias && e.act != ACT_GEGLU && e.act != ACT_HEAD) {
+        constexpr int CH0 = (BN >= 64) ? BN / 2 : BN;
+        bias_s = bias_base + (warp - 4) * 128;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < (CH0 + 31) / 32; ++k)
+          if (lane + 32 * k < CH0) bias_s[lane + 32 * k] = __ldg(e.bias + tile_n * BN + half * CH0 + lane + 32 * k);
+        __syncwarp();
+      }
       mbar_wait(&tfull_bar[g], (it >> 1) & 1);
       fence_after_sync();
       gt_epilogue<T, BN>(e, tmem_base + ((uint32_t)(q * 32) << 16) + g * BN, valid, m, orow, tile_n * BN, tile_n,
-                         stg_base + (warp - 4) * GT_STG_WORDS, lane, half);
+                         stg_base + (warp - 4) * GT_STG_WORDS, lane, half, bias_s);
       fence_before_sync();
       mbar_arrive(&tempty_bar[g]);
     }

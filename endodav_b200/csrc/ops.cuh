@@ -17,6 +17,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "conv_halo.cuh"
 #include "head_fused.cuh"
 
 namespace edv {
@@ -172,7 +173,7 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
   }
   const int kblocks = a.K / BK;
   const int stage_bytes = gt_stage_bytes<BN, BK>();
-  const size_t stg_bytes = 16 * (size_t)GT_STG_WORDS * 4;   // epilogue transposition buffers
+  const size_t stg_bytes = 16 * (size_t)GT_STG_WORDS * 4 + 16 * 128 * 4;   // + per-warp bias slices   // epilogue transposition buffers
   int stages = (int)((220 * 1024 - stg_bytes - 2048) / stage_bytes);  // one persistent CTA per SM owns the shared memory
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
@@ -193,7 +194,36 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
   L.check("gemm_tc");
 }
 
+// 64-channel 3x3 convs with halo reuse (conv_halo.cuh)
+template <typename T, int BN> void launch_conv_halo(Launch& L, const GemmArgs& a) {
+  using namespace tc;
+  auto kern = conv3x3_halo_kernel<T, 64, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem_bytes<64, BN>());
+    attr_done = true;
+  }
+  const int tiles_x = (a.Wd + CH_TW - 1) / CH_TW, tiles_y = (a.H + CH_TH - 1) / CH_TH;
+  const long long total = (long long)a.F * tiles_x * tiles_y;
+  if (total > 0x7fffffffLL) return L.fail(EDV_ERR_ARG, "conv_halo: too many tiles");
+  const int grid = (int)std::min<long long>(total, num_sms());
+  note_gemm(L, a, 2);
+  kern<<<grid, CH_THREADS, ch_smem_bytes<64, BN>(), L.stream>>>((const T*)a.A, (const T*)a.W, a.e, a.F, a.H, a.Wd, tiles_x,
+                                                               tiles_y, (int)total);
+  L.check("conv_halo");
+}
+
+inline bool conv_halo_ok(const GemmArgs& a) {
+  return a.conv && a.stride == 1 && a.C == 64 && (a.N == 64 || a.N == 32) &&
+         (a.e.act == ACT_NONE || a.e.act == ACT_RELU || a.e.act == ACT_SIGMOID) && a.e.map == MAP_LINEAR;
+}
+
 template <typename T> void launch_gemm_tc(Launch& L, int dtype, const GemmArgs& a) {
+  if (conv_halo_ok(a)) {
+    if (a.N == 64) launch_conv_halo<T, 64>(L, a);
+    else launch_conv_halo<T, 32>(L, a);
+    return;
+  }
   const bool small_k = a.conv ? (a.C % 64 != 0) : (a.K % 64 != 0);
   const int bk = small_k ? 32 : 64;
   if ((a.conv ? a.C : a.K) % bk != 0) return L.fail(EDV_ERR_ARG, "gemm_tc: K (or conv C) must be a multiple of 32");
@@ -225,10 +255,33 @@ template <typename T> void launch_gemm_tc(Launch& L, int dtype, const GemmArgs& 
   L.fail(EDV_ERR_ARG, "gemm_tc: no instantiation");
 }
 
+// which compile-time epilogue instantiation (gemm_tc.cuh EF_*) matches this epilogue, or -1
+inline int epi_kind(const Epi& e) {
+  using namespace tc;
+  if (e.rowbias || e.map == MAP_PIXSHUF || e.act == ACT_SIGMOID || e.act == ACT_GEGLU || e.act == ACT_HEAD || !e.out) return -1;
+  if (e.res2 && (e.res2_f32 || !e.res1)) return -1;
+  int f = 0;
+  if (e.bias) f |= EF_BIAS;
+  if (e.act == ACT_GELU) f |= EF_GELU;
+  if (e.act == ACT_RELU) f |= EF_RELU;
+  if (e.res1) f |= e.res1_f32 ? EF_RES1_F32 : EF_RES1_T;
+  if (e.res2) f |= EF_RES2_T;
+  if (e.out_f32) f |= EF_OUT_F32;
+  if (e.out_relu) f |= EF_OUT_RELU;
+  const int known[] = {EF_BIAS, EF_BIAS | EF_GELU, EF_BIAS | EF_RES1_F32 | EF_OUT_F32, EF_BIAS | EF_OUT_F32, EF_BIAS | EF_RES1_F32,
+                       EF_BIAS | EF_RES1_T, EF_BIAS | EF_RES1_T | EF_OUT_RELU, EF_BIAS | EF_RES1_T | EF_RES2_T,
+                       EF_BIAS | EF_RES1_T | EF_RES2_T | EF_OUT_RELU, EF_BIAS | EF_RELU, EF_OUT_RELU};
+  for (int k : known)
+    if (k == f) return f;
+  return -1;
+}
+
 // dispatch on dtype / engine.  GEGLU and HEAD epilogues exist only in the tcgen05 kernel;
 // the CUDA-core path composes them from a plain GEMM plus a small kernel (see engine.cu).
-inline void gemm(Launch& L, int dtype, int engine, const GemmArgs& a) {
+inline void gemm(Launch& L, int dtype, int engine, const GemmArgs& a_in) {
   if (!L.ok()) return;
+  GemmArgs a = a_in;
+  a.e.kind = epi_kind(a.e);
   if (dtype == EDV_F32) return launch_gemm_simt<float>(L, a);
   if (engine == EDV_ENGINE_SIMT) {
     if (dtype == EDV_BF16) return launch_gemm_simt<bf16>(L, a);

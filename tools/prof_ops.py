@@ -33,6 +33,8 @@ for w in which:
         elif w == "head":
             eng.op_disp_head(rnd(32, 296, 296, 32), rnd(32, 288, scale=0.06), torch.zeros(32).cuda(),
                              torch.ones(33).cuda() * 0.1, 518, 518)
+        elif w == "oc":
+            eng.op_conv3x3(rnd(32, 296, 296, 64), rnd(32, 576, scale=0.04), torch.zeros(32).cuda(), False)
         elif w == "tattn":
             eng.op_temporal_attention(rnd(32 * 5476, 192, scale=0.7), 1, 32, 5476, 64)
     torch.cuda.synchronize()
