@@ -12,48 +12,56 @@
 template <typename T, bool U8>
 __global__ void preprocess_patches_kernel(const void* __restrict__ src, T* __restrict__ out, int F, int H, int W,
                                           int h, int w, int Kp) {
+  // one thread = 8 consecutive k of one patch row (one aligned 16-byte store for 16-bit T)
   const int ph = h / 14, pw = w / 14;
-  const long long total = (long long)F * ph * pw * Kp;
+  const int kch = Kp / 8;
+  const long long total = (long long)F * ph * pw * kch;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k0 = (int)(i % kch) * 8;
+  const long long row = i / kch;
+  const int px = (int)(row % pw);
+  const long long t = row / pw;
+  const int py = (int)(t % ph);
+  const int f = (int)(t / ph);
   const float sy = (h > 1) ? (float)(H - 1) / (float)(h - 1) : 0.f;
   const float sx = (w > 1) ? (float)(W - 1) / (float)(w - 1) : 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(i % Kp);
-    long long row = i / Kp;
-    float val = 0.f;
-    if (k < 588) {
-      int c = k / 196, r = k - c * 196;
-      int ky = r / 14, kx = r - ky * 14;
-      int px = (int)(row % pw);
-      long long t = row / pw;
-      int py = (int)(t % ph);
-      int f = (int)(t / ph);
-      int y = py * 14 + ky, x = px * 14 + kx;
+  int c = k0 / 196, r = k0 - c * 196;
+  int ky = r / 14, kx = r - ky * 14;
+  float val[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float o = 0.f;
+    if (k0 + j < 588) {
+      const int y = py * 14 + ky, x = px * 14 + kx;
       float v;
       if (U8) {
         // uint8 HWC frames already at network resolution (infer_video_depth path)
-        const uint8_t* s = (const uint8_t*)src;
-        v = (float)s[(((long long)f * H + y) * W + x) * 3 + c] / 255.0f;
+        const uint8_t* sp = (const uint8_t*)src;
+        v = (float)sp[(((long long)f * H + y) * W + x) * 3 + c] / 255.0f;
       } else {
-        const float* s = (const float*)src + ((long long)f * 3 + c) * H * W;
+        const float* sp = (const float*)src + ((long long)f * 3 + c) * H * W;
         if (H == h && W == w) {
-          v = s[(long long)y * W + x];
+          v = sp[(long long)y * W + x];
         } else {
           // area_pixel_compute_source_index with align_corners=True
-          float fy = sy * y, fx = sx * x;
-          int y0 = (int)fy, x0 = (int)fx;
-          int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-          float ly = fy - y0, lx = fx - x0;
-          float v00 = s[(long long)y0 * W + x0], v01 = s[(long long)y0 * W + x1];
-          float v10 = s[(long long)y1 * W + x0], v11 = s[(long long)y1 * W + x1];
+          const float fy = sy * y, fx = sx * x;
+          const int y0 = (int)fy, x0 = (int)fx;
+          const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+          const float ly = fy - y0, lx = fx - x0;
+          const float v00 = sp[(long long)y0 * W + x0], v01 = sp[(long long)y0 * W + x1];
+          const float v10 = sp[(long long)y1 * W + x0], v11 = sp[(long long)y1 * W + x1];
           v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
         }
       }
       const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
       const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-      val = (v - mean) / stdv;
+      o = (v - mean) / stdv;
     }
-    out[i] = from_f<T>(val);
+    val[j] = o;
+    if (++kx == 14) { kx = 0; if (++ky == 14) { ky = 0; ++c; } }
   }
+  store_vec<T, 8>(out + row * Kp + k0, val);
 }
 
 // cls row of every frame: x[f, 0, :] = cls_token + pos_embed[0]  (vision_transformer.py:225-227)
@@ -71,51 +79,75 @@ __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ 
 // (vision_transformer.py:318-321).  Two-pass statistics in registers.
 // ---------------------------------------------------------------------------------------
 template <typename TOut, int MAXV>
-__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, TOut* __restrict__ out, long long Mout, int D,
-                                 float eps, int grp, int skip) {
-  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, TOut* __restrict__ out,
+                                                        long long Mout, int D, float eps, int grp, int skip) {
+  // one warp normalises TWO consecutive rows: both rows' loads are in flight before the first
+  // reduction (the kernel is pure streaming: fp32 in, 16-bit out)
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= Mout) return;
-  long long mo = warp, mi = mo;
-  if (grp > 0) {
-    int per = grp - skip;
-    mi = (mo / per) * grp + skip + (mo % per);
-  }
-  const float* xr = x + mi * D;
-  float v[MAXV * 4];
-  float s = 0.f;
+  const long long mo0 = warp * 2;
+  if (mo0 >= Mout) return;
+  float v[2][MAXV * 4];
+  bool live[2];
+  long long mo[2];
 #pragma unroll
-  for (int it = 0; it < MAXV; ++it) {
-    int c = (it * 32 + lane) * 4;
-    if (c < D) {
-      float4 t = *reinterpret_cast<const float4*>(xr + c);
-      v[4 * it] = t.x; v[4 * it + 1] = t.y; v[4 * it + 2] = t.z; v[4 * it + 3] = t.w;
-      s += t.x + t.y + t.z + t.w;
-    } else {
-      v[4 * it] = v[4 * it + 1] = v[4 * it + 2] = v[4 * it + 3] = 0.f;
+  for (int rw = 0; rw < 2; ++rw) {
+    mo[rw] = mo0 + rw;
+    live[rw] = mo[rw] < Mout;
+    long long mi = mo[rw];
+    if (grp > 0) {
+      const int per = grp - skip;
+      mi = (mo[rw] / per) * grp + skip + (mo[rw] % per);
+    }
+    const float* xr = x + mi * D;
+#pragma unroll
+    for (int it = 0; it < MAXV; ++it) {
+      const int c = (it * 32 + lane) * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[rw] && c < D) t = *reinterpret_cast<const float4*>(xr + c);
+      v[rw][4 * it] = t.x; v[rw][4 * it + 1] = t.y; v[rw][4 * it + 2] = t.z; v[rw][4 * it + 3] = t.w;
     }
   }
-  const float mean = warp_sum(s) / (float)D;
-  float q = 0.f;
+  float g[MAXV * 4], b[MAXV * 4];
 #pragma unroll
   for (int it = 0; it < MAXV; ++it) {
-    int c = (it * 32 + lane) * 4;
+    const int c = (it * 32 + lane) * 4;
+    float4 tg = make_float4(0.f, 0.f, 0.f, 0.f), tb = tg;
     if (c < D) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { float d = v[4 * it + j] - mean; q += d * d; }
+      tg = *reinterpret_cast<const float4*>(gamma + c);
+      tb = *reinterpret_cast<const float4*>(beta + c);
     }
+    g[4 * it] = tg.x; g[4 * it + 1] = tg.y; g[4 * it + 2] = tg.z; g[4 * it + 3] = tg.w;
+    b[4 * it] = tb.x; b[4 * it + 1] = tb.y; b[4 * it + 2] = tb.z; b[4 * it + 3] = tb.w;
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-  TOut* orow = out + mo * D;
 #pragma unroll
-  for (int it = 0; it < MAXV; ++it) {
-    int c = (it * 32 + lane) * 4;
-    if (c < D) {
-      float o[4];
+  for (int rw = 0; rw < 2; ++rw) {
+    float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = (v[4 * it + j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
-      store_vec<TOut, 4>(orow + c, o);
+    for (int i = 0; i < MAXV * 4; ++i) s += v[rw][i];     // columns >= D hold zeros
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < MAXV; ++it) {
+      const int c = (it * 32 + lane) * 4;
+      if (c < D) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float d = v[rw][4 * it + j] - mean; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (!live[rw]) continue;
+    TOut* orow = out + mo[rw] * D;
+#pragma unroll
+    for (int it = 0; it < MAXV; ++it) {
+      const int c = (it * 32 + lane) * 4;
+      if (c < D) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (v[rw][4 * it + j] - mean) * rstd * g[4 * it + j] + b[4 * it + j];
+        store_vec<TOut, 4>(orow + c, o);
+      }
     }
   }
 }

@@ -317,7 +317,7 @@ struct Fwd {
     float* x = (float*)buf("x");
     {
       long long tot = p.Mp * KPATCH;
-      unsigned blocks = nblk(tot, 256);
+      unsigned blocks = nblk(tot / 8, 256);
       L.note(0, (double)p.BT * 3 * p.H * p.W * (u8 ? 1 : 4) + (double)tot * es);
       EDV_DISPATCH_T(dt, {
         if (u8) preprocess_patches_kernel<T, true><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH);

@@ -69,7 +69,7 @@ template <typename T> __device__ __forceinline__ float4 ld4_as_f32(const void* p
 // (ncu: stall_no_inst on every other line, ~2 500 cycles per 32-column chunk).  The hot call sites
 // of the forward therefore get straight-line instantiations (F >= 0: bit mask below); anything
 // else (row-bias tables, pixel shuffle, sigmoid) runs the generic F = -1 version.
-enum { EF_BIAS = 1, EF_GELU = 2, EF_RELU = 4, EF_RES1_F32 = 8, EF_RES1_T = 16, EF_RES2_T = 32, EF_OUT_F32 = 64, EF_OUT_RELU = 128 };
+enum { EF_BIAS = 1, EF_GELU = 2, EF_RELU = 4, EF_RES1_F32 = 8, EF_RES1_T = 16, EF_RES2_T = 32, EF_OUT_F32 = 64, EF_OUT_RELU = 128, EF_ROWBIAS = 256 };
 
 // The fused epilogue on NS row segments (4 consecutive columns starting at n of rows mm[it] ->
 // output rows oo[it], oo < 0 = masked).  Same order of operations as epi_apply (common.cuh):
@@ -96,7 +96,8 @@ __device__ __forceinline__ void gt_applyN(const Epi& e, float4* a, const int* mm
 #pragma unroll
     for (int it = 0; it < NS; ++it) f4_add(a[it], b);
   }
-  if (!S && e.rowbias) {
+  const bool has_rowbias = S ? ((F & EF_ROWBIAS) != 0) : (e.rowbias != nullptr);
+  if (has_rowbias) {
 #pragma unroll
     for (int it = 0; it < NS; ++it)
       if (oo[it] >= 0) f4_add(a[it], *reinterpret_cast<const float4*>(e.rowbias + (long long)((mm[it] / e.rb_div) % e.rb_mod) * e.rb_ld + n));
@@ -287,6 +288,7 @@ __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool va
       EDV_EPI_CASE(EF_BIAS | EF_RES1_T | EF_RES2_T | EF_OUT_RELU)
       EDV_EPI_CASE(EF_BIAS | EF_RELU)                                    // RCU conv1
       EDV_EPI_CASE(EF_OUT_RELU)                                          // layer*_rn
+      EDV_EPI_CASE(EF_ROWBIAS)                                           // temporal q|k|v with the folded PE table
 #undef EDV_EPI_CASE
       default: gt_epi_rows<T, BN, -1>(e, trow, m32, o32, n0, stg, lane, half, bias_s); break;
     }
