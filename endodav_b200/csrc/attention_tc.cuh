@@ -6,7 +6,7 @@
 // One CTA handles 256 queries (two 128-row tiles, A and B) of one (frame, head) and streams the
 // keys/values of that (frame, head) in 128-row tiles.  384 threads = 3 warpgroups; setmaxnreg
 // moves registers from warpgroup 0 (56/thread) to the softmax warpgroups (224/thread):
-//   warp 0       TMA producer: Q tiles once, then K_j | V_j into a 3-stage 128B-swizzled ring
+//   warp 0       TMA producer: Q tiles once, then K_j | V_j into a 4-stage 128B-swizzled ring
 //   warp 1       TMEM allocator + MMA issuer (one lane):  S_t = Q_t K_j^T  (SS, 128x128x64) and
 //                O_t += P_t V_j (A = P from TMEM, B = V tile read MN-major, 128x64x128)
 //   warps 2,3    idle (fill warpgroup 0)
@@ -15,8 +15,11 @@
 //                entirely thread-local (no shuffles), P rounded to 16 bit and written back to
 //                TMEM with tcgen05.st, O rescaled in TMEM only when the running max grew by
 //                more than 2^8 (lazy rescale), final O / l written straight to global.
-// The two tiles ping-pong: while warpgroup A is in its softmax, the tensor core computes
-// S_B / O_B and vice versa; the kernel is MUFU(ex2)-bound at head dim 64.
+// Software pipeline: S_t(j+1) = Q_t K_{j+1}^T is issued as soon as warpgroup t has pulled S_t(j)
+// into registers (barrier s_free), i.e. it runs UNDER the softmax of S_t(j); O_t += P_t(j) V_j
+// follows when P_t(j) is in TMEM (p_full) and its completion (pv_done) gates only the next P
+// store / O rescale.  So a warpgroup's iteration is just its softmax; the kernel is MUFU(ex2)
+// bound at head dim 64.
 //
 // TMEM columns (512): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
 #pragma once
@@ -29,7 +32,7 @@ namespace tc {
 constexpr int FA_BM = 128;      // query rows per tile
 constexpr int FA_BN = 128;      // keys per iteration
 constexpr int FA_HD = 64;
-constexpr int FA_STAGES = 3;
+constexpr int FA_STAGES = 4;
 constexpr int FA_THREADS = 384;
 constexpr uint32_t FA_TILE_BYTES = FA_BM * FA_HD * 2;  // 16 KB: one 128 x 64 16-bit tile
 constexpr size_t FA_SMEM = 1024 + (2 + 2 * FA_STAGES) * (size_t)FA_TILE_BYTES + 256;
@@ -86,7 +89,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   uint64_t* s_full = kv_empty + FA_STAGES; // 2
   uint64_t* p_full = s_full + 2;           // 2
   uint64_t* o_done = p_full + 2;           // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_free = o_done + 2;           // 2: warpgroup t holds S_t(j) in registers
+  uint64_t* pv_done = s_free + 2;          // 2: O_t += P_t(j) V_j has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.z, h = blockIdx.y;
@@ -107,6 +112,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 128);
       mbar_init(&o_done[t], 1);
+      mbar_init(&s_free[t], 128);
+      mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -157,27 +164,29 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       for (int j = 0; j < n_iter; ++j) {
         const int s = j % FA_STAGES;
         const uint32_t va = smem_u32(sKV + (size_t)s * 2 * FA_TILE_BYTES + FA_TILE_BYTES);
+        // 1) S_t(j+1): as soon as warpgroup t holds S_t(j) in registers and K_{j+1} has landed
+        if (j + 1 < n_iter) {
+          const int s1 = (j + 1) % FA_STAGES;
+          mbar_wait(&kv_full[s1], ((j + 1) / FA_STAGES) & 1);
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait(&s_free[t], j & 1);
+            fence_after_sync();
+            issue_qk(t, s1);
+          }
+        }
+        // 2) O_t (+)= P_t(j) V_j : A from TMEM (8 columns per 16-key step), B rows = keys (MN-major,
+        //    128 B per key, 8-key groups 1024 B apart) -> +2048 B per 16-key step
         for (int t = 0; t < nt; ++t) {
-          mbar_wait(&p_full[t], j & 1);   // P_t(j) in TMEM, O_t rescaled, S_t consumed
+          mbar_wait(&p_full[t], j & 1);   // P_t(j) in TMEM, O_t rescaled
           fence_after_sync();
-          // O_t (+)= P_t V_j : A from TMEM (8 columns per 16-key step), B rows = keys (MN-major,
-          // 128 B per key, 8-key groups 1024 B apart) -> +2048 B per 16-key step
           const uint64_t vdesc = make_smem_desc(va, 1024, 1024, SWZ_128B);
 #pragma unroll
           for (int k = 0; k < FA_BN / 16; ++k)
             mma_ts(tmem_base + 256 + t * FA_HD, tmem_base + 384 + t * 64 + k * 8, vdesc + (uint64_t)(128 * k), idesc_pv,
                    (j | k) ? 1u : 0u);
+          mma_commit(&pv_done[t]);
           if (t == nt - 1) mma_commit(&kv_empty[s]);   // K_j and V_j no longer needed once these complete
-          if (j + 1 < n_iter) {
-            const int s1 = (j + 1) % FA_STAGES;
-            if (t == 0) {
-              mbar_wait(&kv_full[s1], ((j + 1) / FA_STAGES) & 1);
-              fence_after_sync();
-            }
-            issue_qk(t, s1);
-          } else {
-            mma_commit(&o_done[t]);
-          }
+          if (j + 1 == n_iter) mma_commit(&o_done[t]);
         }
       }
     }
@@ -205,6 +214,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         tmem_ld32_nowait(tS + 64, sv + 64);
         tmem_ld32_nowait(tS + 96, sv + 96);
         tmem_ld_wait();
+        fence_before_sync();
+        mbar_arrive(&s_free[t]);          // S_t(j) is in registers: the tensor core may overwrite it with S_t(j+1)
         const int valid = S - j * FA_BN;  // keys of this tile that belong to the frame
         if (valid < FA_BN) {
 #pragma unroll
@@ -226,8 +237,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           m_used = mx;
           l *= factor;
         }
+        if (j > 0) {
+          mbar_wait(&pv_done[t], (j - 1) & 1);   // O_t += P_t(j-1) V_{j-1} done: O_t stable, P_t free
+          fence_after_sync();
+        }
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
-          // PV(j-1) has completed (s_full(j) was committed after it), so O_t is stable
 #pragma unroll
           for (int c = 0; c < FA_HD; c += 32) {
             uint32_t ov[32];

@@ -81,7 +81,8 @@ __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ 
 template <typename TOut, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, TOut* __restrict__ out,
-                                                        long long Mout, int D, float eps, int grp, int skip) {
+                                                        long long Mout, int D, float eps, int grp, int skip,
+                                                        const float* __restrict__ add, int add_div, int add_mod) {
   // one warp normalises TWO consecutive rows: both rows' loads are in flight before the first
   // reduction (the kernel is pure streaming: fp32 in, 16-bit out)
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -139,6 +140,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
     if (!live[rw]) continue;
     TOut* orow = out + mo[rw] * D;
+    // optional per-frame additive table (temporal positional encoding, motion_module.py:236-237)
+    const float* arow = add ? add + (long long)((mo[rw] / add_div) % add_mod) * D : nullptr;
 #pragma unroll
     for (int it = 0; it < MAXV; ++it) {
       const int c = (it * 32 + lane) * 4;
@@ -146,6 +149,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = (v[rw][4 * it + j] - mean) * rstd * g[4 * it + j] + b[4 * it + j];
+        if (arow) {
+          const float4 t = *reinterpret_cast<const float4*>(arow + c);
+          o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+        }
         store_vec<TOut, 4>(orow + c, o);
       }
     }

@@ -184,16 +184,10 @@ struct Fwd {
     }
     for (int a = 0; a < 2; ++a) {
       const std::string an = n + "a" + std::to_string(a) + ".";
-      layernorm(L, dt, hs, wf(an + "ln.w", C), wf(an + "ln.b", C), lnb, Mm, C, 1e-5f);
-      {
-        // q|k|v in one GEMM; (x + pe) W = x W + pe W -> per-frame additive table
-        Epi e = ep(qkvb, 3 * C, nullptr);
-        if (!c->cfg.rope) {
-          e.rowbias = wf(an + "petab", (size_t)T * 3 * C);
-          e.rb_div = hw; e.rb_mod = T; e.rb_ld = 3 * C;
-        }
-        linear(lnb, Mm, C, an + "qkv.w", 3 * C, e);
-      }
+      // LN, + sinusoidal PE of the row's frame (motion_module.py:236-237), then q|k|v in one GEMM
+      layernorm(L, dt, hs, wf(an + "ln.w", C), wf(an + "ln.b", C), lnb, Mm, C, 1e-5f, 0, 0,
+                c->cfg.rope ? nullptr : wf(an + "pe", (size_t)T * C), hw, T);
+      linear(lnb, Mm, C, an + "qkv.w", 3 * C, ep(qkvb, 3 * C, nullptr));
       temporal_attention(L, dt, qkvb, att, B, T, hw, C);
       {
         Epi e = ep(hs, C, wf(an + "out.b", C));

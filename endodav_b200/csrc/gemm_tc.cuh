@@ -288,7 +288,7 @@ __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool va
       EDV_EPI_CASE(EF_BIAS | EF_RES1_T | EF_RES2_T | EF_OUT_RELU)
       EDV_EPI_CASE(EF_BIAS | EF_RELU)                                    // RCU conv1
       EDV_EPI_CASE(EF_OUT_RELU)                                          // layer*_rn
-      EDV_EPI_CASE(EF_ROWBIAS)                                           // temporal q|k|v with the folded PE table
+      EDV_EPI_CASE(0)                                                    // temporal q|k|v (no bias)
 #undef EDV_EPI_CASE
       default: gt_epi_rows<T, BN, -1>(e, trow, m32, o32, n0, stg, lane, half, bias_s); break;
     }

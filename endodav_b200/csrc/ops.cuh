@@ -258,11 +258,10 @@ template <typename T> void launch_gemm_tc(Launch& L, int dtype, const GemmArgs& 
 // which compile-time epilogue instantiation (gemm_tc.cuh EF_*) matches this epilogue, or -1
 inline int epi_kind(const Epi& e) {
   using namespace tc;
-  if (e.map == MAP_PIXSHUF || e.map == MAP_TOKENS || e.act == ACT_SIGMOID || e.act == ACT_GEGLU || e.act == ACT_HEAD || !e.out) return -1;
+  if (e.rowbias || e.map == MAP_PIXSHUF || e.act == ACT_SIGMOID || e.act == ACT_GEGLU || e.act == ACT_HEAD || !e.out) return -1;
   if (e.res2 && (e.res2_f32 || !e.res1)) return -1;
   int f = 0;
   if (e.bias) f |= EF_BIAS;
-  if (e.rowbias) f |= EF_ROWBIAS;
   if (e.act == ACT_GELU) f |= EF_GELU;
   if (e.act == ACT_RELU) f |= EF_RELU;
   if (e.res1) f |= e.res1_f32 ? EF_RES1_F32 : EF_RES1_T;
@@ -271,7 +270,7 @@ inline int epi_kind(const Epi& e) {
   if (e.out_relu) f |= EF_OUT_RELU;
   const int known[] = {EF_BIAS, EF_BIAS | EF_GELU, EF_BIAS | EF_RES1_F32 | EF_OUT_F32, EF_BIAS | EF_OUT_F32, EF_BIAS | EF_RES1_F32,
                        EF_BIAS | EF_RES1_T, EF_BIAS | EF_RES1_T | EF_OUT_RELU, EF_BIAS | EF_RES1_T | EF_RES2_T,
-                       EF_BIAS | EF_RES1_T | EF_RES2_T | EF_OUT_RELU, EF_BIAS | EF_RELU, EF_OUT_RELU, EF_ROWBIAS};
+                       EF_BIAS | EF_RES1_T | EF_RES2_T | EF_OUT_RELU, EF_BIAS | EF_RELU, EF_OUT_RELU, 0};
   for (int k : known)
     if (k == f) return f;
   return -1;
@@ -303,18 +302,19 @@ inline void gemm(Launch& L, int dtype, int engine, const GemmArgs& a_in) {
 inline unsigned nblk(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
 inline void layernorm(Launch& L, int dtype, const float* x, const float* g, const float* b, void* y, long long Mout,
-                      int D, float eps, int grp = 0, int skip = 0) {
+                      int D, float eps, int grp = 0, int skip = 0, const float* add = nullptr, int add_div = 1,
+                      int add_mod = 1) {
   if (!L.ok()) return;
   if (D % 4 != 0 || D > 1024) return L.fail(EDV_ERR_ARG, "layernorm: D must be a multiple of 4 and <= 1024");
   const int maxv = (D + 127) / 128;
   const unsigned blocks = nblk(((Mout + 1) / 2) * 32, 256);   // one warp per two rows
   L.note(0, (double)Mout * D * (4 + dtype_size(dtype)));
   EDV_DISPATCH_T(dtype, {
-    if (maxv <= 1) layernorm_kernel<T, 1><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
-    else if (maxv <= 2) layernorm_kernel<T, 2><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
-    else if (maxv <= 3) layernorm_kernel<T, 3><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
-    else if (maxv <= 4) layernorm_kernel<T, 4><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
-    else layernorm_kernel<T, 8><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip);
+    if (maxv <= 1) layernorm_kernel<T, 1><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else if (maxv <= 2) layernorm_kernel<T, 2><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else if (maxv <= 3) layernorm_kernel<T, 3><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else if (maxv <= 4) layernorm_kernel<T, 4><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else layernorm_kernel<T, 8><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
   });
   L.check("layernorm");
 }

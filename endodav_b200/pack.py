@@ -12,8 +12,8 @@ What is folded at pack time (all exact in real arithmetic, done in float64):
   * q * head_dim**-0.5 into the q rows of qkv (attention.py:60; motion attention.py:187-188)
   * projects[i] (1x1) composed with resize_layers[i] (ConvTranspose k==stride) for i=0,1
     into one GEMM whose columns are (ky,kx,c) -> pixel shuffle (dpt.py:60-83)
-  * temporal q|k|v concatenated; (x+pe)W = xW + peW -> per-frame bias table
-    (motion_module.py:189-197,236-237)
+  * temporal q|k|v concatenated into one [3C, C] GEMM; the sinusoidal PE rows [T, C] are kept
+    as a table that the LayerNorm kernel adds to its output (motion_module.py:189-197,236-237)
   * GEGLU projection rows paired per 128-column tile [64 value | 64 gate]
     (motion_module/attention.py:382-384)
 Conv weights go to (out, ky, kx, c) order with channels padded to multiples of 64.
@@ -222,7 +222,7 @@ def pack_state_dict(sd, cfg, dtype=torch.bfloat16):
             mat(an + "qkv.w", qkv)
             if cfg.get("pe", "ape") == "ape":
                 pe = sd[ab + "pos_encoder.pe"].double()[0, :T]      # [T, C]
-                vec(an + "petab", pe @ qkv.t())
+                vec(an + "pe", pe)     # added to the LayerNorm output of frame f (motion_module.py:236-237)
             mat(an + "out.w", sd[ab + "to_out.0.weight"])
             vec(an + "out.b", sd[ab + "to_out.0.bias"])
         vec(n + "ffln.w", sd[tb + "ff_norm.weight"])

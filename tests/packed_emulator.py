@@ -120,10 +120,10 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
         for a in range(2):
             an = n + "a%d." % a
             ln = F.layer_norm(hs, (C,), pk[an + "ln.w"], pk[an + "ln.b"], 1e-5)
-            qkv = _lin(ln, pk[an + "qkv.w"])
-            if (an + "petab") in pk:
+            if (an + "pe") in pk:
                 frame = (torch.arange(Fr * hw) // hw) % T
-                qkv = qkv + pk[an + "petab"][frame]
+                ln = ln + pk[an + "pe"][frame]
+            qkv = _lin(ln, pk[an + "qkv.w"])
             q, k, v = qkv.reshape(B, T, hw, 3, 8, hd).permute(3, 0, 2, 4, 1, 5)  # [B,hw,8,T,hd]
             o = (q @ k.transpose(-1, -2)).softmax(-1) @ v
             o = o.permute(0, 3, 1, 2, 4).reshape(Fr * hw, C)

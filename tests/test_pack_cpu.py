@@ -110,7 +110,7 @@ def test_pack_dtypes_and_alignment():
         pk = pack.pack_state_dict(sd, cfg, dt)
         for k, v in pk.items():
             assert v.is_contiguous()
-            if v.dim() == 2 and not k.endswith("petab"):
+            if v.dim() == 2 and not k.endswith(".pe"):
                 assert v.dtype == dt, k
                 assert v.shape[1] % 32 == 0, (k, v.shape)   # K of every GEMM is a multiple of 32
                 assert v.shape[0] % 32 == 0, (k, v.shape)   # N of every GEMM is a multiple of 32
