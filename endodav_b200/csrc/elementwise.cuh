@@ -203,6 +203,61 @@ __global__ void groupnorm_stats_kernel(const T* __restrict__ x, float2* __restri
   }
 }
 
+// Coalesced statistics for the 16-bit paths: grid (F, NSPLIT); a block streams whole pixel rows
+// (16-byte loads), keeps per-thread sums of its 8 channels and reduces them through shared memory
+// in a FIXED order (no atomics: the forward must stay bit-reproducible) to one (sum, sum of
+// squares) per group, written to part[(f*NSPLIT + split)*32 + g].  fp32 sums over <= a few 10^4
+// values of O(1): the E[x^2]-E[x]^2 form is far inside 16-bit accuracy.
+template <typename T>
+__global__ void __launch_bounds__(256) groupnorm_partial_kernel(const T* __restrict__ x, float2* __restrict__ part, int hw, int C) {
+  __shared__ float cs[2][2048];                // [sum|sq][pixel lane][channel], per_px * C <= 2048
+  const int f = blockIdx.x;
+  const int c8n = C / 8;                       // 16-byte chunks per pixel
+  const int cpg = C / 32;
+  const int per_px = blockDim.x / c8n;         // pixel lanes per block
+  const int c8 = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+  if (pl < per_px) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    const T* base = x + (long long)f * hw * C + c8 * 8;
+    for (int p = blockIdx.y * per_px + pl; p < hw; p += gridDim.y * per_px) {
+      float v[8];
+      load_vec<T, 8>(base + (long long)p * C, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { cs[0][pl * C + c8 * 8 + j] = s[j]; cs[1][pl * C + c8 * 8 + j] = q[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;
+    float a = 0.f;
+    for (int pp = 0; pp < per_px; ++pp)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += cs[which][pp * C + c];
+    float* dst = reinterpret_cast<float*>(&part[((long long)f * gridDim.y + blockIdx.y) * 32 + g]);
+    dst[which] = a;
+  }
+}
+
+// partial (sum, sumsq) over the splits (fixed order) -> (mean, rstd) in stats[f*32+g]
+__global__ void groupnorm_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int n, int nsplit,
+                                          float count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = i >> 5, g = i & 31;
+  float sx = 0.f, sq = 0.f;
+  for (int k = 0; k < nsplit; ++k) {
+    const float2 r = part[((long long)f * nsplit + k) * 32 + g];
+    sx += r.x;
+    sq += r.y;
+  }
+  const float mean = sx / count;
+  const float var = fmaxf(sq / count - mean * mean, 0.f);
+  stats[i] = make_float2(mean, rsqrtf(var + eps));
+}
+
 template <typename T>
 __global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __restrict__ stats,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,

@@ -120,13 +120,22 @@ struct Fwd {
   const float* wf(const std::string& name, size_t n) { return (const float*)w(name, n * 4); }
   const void* wt(const std::string& name, size_t n) { return w(name, n * es); }
 
-  // call-site tag for the profiler: the packed weight name without indices ("blk3.qkv.w" -> "blk.qkv")
+  // call-site tag for the profiler: the packed weight name without its indices
+  // ("blk3.fc1.w" -> "blk.fc1", "ref1.rcu2.c1.w" -> "ref.rcu.c1")
   static std::string tag_of(const std::string& wname) {
-    std::string t;
-    for (char ch : wname)
-      if (ch < '0' || ch > '9') t.push_back(ch);
+    std::string t = wname;
     if (t.size() > 2 && t.compare(t.size() - 2, 2, ".w") == 0) t.resize(t.size() - 2);
-    return t;
+    std::string o;
+    for (size_t i = 0; i < t.size(); ++i) {
+      const bool digit = t[i] >= '0' && t[i] <= '9';
+      if (digit) {
+        size_t j = i;
+        while (j < t.size() && t[j] >= '0' && t[j] <= '9') ++j;
+        if (j < t.size() && t[j] == '.') { i = j - 1; continue; }   // an index token: drop it
+      }
+      o.push_back(t[i]);
+    }
+    return o;
   }
 
   // ---- building blocks --------------------------------------------------------------------
@@ -653,7 +662,7 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
     mm4 = std::max(mm4, rows * 4 * C);
     mm8 = std::max(mm8, rows * 8 * C);
   }
-  add("mm.stats", (size_t)p.BT * 32 * sizeof(float2));
+  add("mm.stats", (size_t)p.BT * 32 * (1 + GN_MAX_SPLIT) * sizeof(float2));
   add("mm.gn", mmC * es);
   add("mm.hs", mmC * 4);
   add("mm.ln", mmC * es);
@@ -889,7 +898,7 @@ int edv_op_groupnorm(int dtype, const void* X, const float* gamma, const float* 
   Launch L;
   L.stream = (cudaStream_t)stream;
   float2* stats = nullptr;
-  if (cudaMallocAsync((void**)&stats, (size_t)F * 32 * sizeof(float2), L.stream) != cudaSuccess) return EDV_ERR_CUDA;
+  if (cudaMallocAsync((void**)&stats, (size_t)F * 32 * (1 + GN_MAX_SPLIT) * sizeof(float2), L.stream) != cudaSuccess) return EDV_ERR_CUDA;
   groupnorm(L, dtype, X, gamma, beta, Y, stats, F, hw, C, eps);
   cudaFreeAsync(stats, L.stream);
   return finish(L);

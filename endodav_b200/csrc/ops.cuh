@@ -319,14 +319,34 @@ inline void layernorm(Launch& L, int dtype, const float* x, const float* g, cons
   L.check("layernorm");
 }
 
+constexpr int GN_MAX_SPLIT = 64;   // groupnorm stats scratch: F*32*(1+GN_MAX_SPLIT) float2
+
 inline void groupnorm(Launch& L, int dtype, const void* x, const float* g, const float* b, void* y, float2* stats,
                       int F, int hw, int C, float eps) {
   if (!L.ok()) return;
   if (C % 32 != 0 || C % 8 != 0) return L.fail(EDV_ERR_ARG, "groupnorm: C must be a multiple of 32");
-  EDV_DISPATCH_T(dtype, {
-    L.note(0, (double)F * hw * C * sizeof(T));
-    groupnorm_stats_kernel<T><<<dim3(32, F), 256, 0, L.stream>>>((const T*)x, stats, hw, C, eps);
+  if (dtype == EDV_F32 || C / 8 > 256) {
+    // fp32 path: two-pass (mean, then centred variance) per (frame, group)
+    EDV_DISPATCH_T(dtype, {
+      L.note(0, (double)F * hw * C * sizeof(T));
+      groupnorm_stats_kernel<T><<<dim3(32, F), 256, 0, L.stream>>>((const T*)x, stats, hw, C, eps);
+    });
     L.check("groupnorm_stats");
+  } else {
+    const int per_px = 256 / (C / 8);
+    int split = (hw + per_px * 8 - 1) / (per_px * 8);     // ~8 pixels per thread
+    if (split < 1) split = 1;
+    if (split > GN_MAX_SPLIT) split = GN_MAX_SPLIT;
+    float2* part = stats + (size_t)F * 32;                 // caller provides F*32*(1+GN_MAX_SPLIT) entries
+    EDV_DISPATCH_T(dtype, {
+      L.note(0, (double)F * hw * C * sizeof(T));
+      groupnorm_partial_kernel<T><<<dim3(F, split), 256, 0, L.stream>>>((const T*)x, part, hw, C);
+    });
+    L.check("groupnorm_stats");
+    groupnorm_finalize_kernel<<<nblk((long long)F * 32, 256), 256, 0, L.stream>>>(part, stats, F * 32, split, (float)hw * (C / 32), eps);
+    L.check("groupnorm_finalize");
+  }
+  EDV_DISPATCH_T(dtype, {
     long long total8 = (long long)F * hw * C / 8;
     L.note(0, 2.0 * F * hw * C * sizeof(T));
     groupnorm_apply_kernel<T><<<nblk(total8, 256), 256, 0, L.stream>>>((const T*)x, stats, g, b, (T*)y, total8, hw, C);
