@@ -19,12 +19,15 @@
 // into registers (barrier s_free), i.e. it runs UNDER the softmax of S_t(j); O_t += P_t(j) V_j
 // follows when P_t(j) is in TMEM (p_full) and its completion (pv_done) gates only the next P
 // store / O rescale.  So a warpgroup's iteration is just its softmax; the kernel is MUFU(ex2)
-// bound at head dim 64.
+// bound at head dim 64 in theory; in practice (ncu + in-kernel timers) it is bound by
+// the tensor pipe running these small MMAs at ~45 % of their floor plus softmax issue latency.
 //
 // TMEM columns (512): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
 #pragma once
 #include "attention_simt.cuh"
 #include "launch.h"
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace tc {
@@ -34,6 +37,7 @@ constexpr int FA_BN = 128;      // keys per iteration
 constexpr int FA_HD = 64;
 constexpr int FA_STAGES = 4;
 constexpr int FA_THREADS = 384;
+constexpr int FA_POLY_DEFAULT = 0;   // measured: the polynomial path only adds issue pressure (0: all MUFU)
 constexpr uint32_t FA_TILE_BYTES = FA_BM * FA_HD * 2;  // 16 KB: one 128 x 64 16-bit tile
 constexpr size_t FA_SMEM = 1024 + (2 + 2 * FA_STAGES) * (size_t)FA_TILE_BYTES + 256;
 
@@ -41,6 +45,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-4
+// polynomial for 2^f (max relative error 7e-6, far below the 16-bit rounding of P), exponent added
+// with an integer shift.  Used for every PM-th score so that the ex2 work is shared between the
+// XU pipe (16 lanes/clk/SM) and the otherwise idle FMA pipe -- softmax at head dim 64 is MUFU-bound.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;              // 1.5 * 2^23: n lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.009666374f, f, 0.055838343f);
+  p = fmaf(p, f, 0.24022348f);
+  p = fmaf(p, f, 0.69313675f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 __device__ __forceinline__ uint32_t pack_pair(float a, float b, bf16) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -75,7 +93,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
-template <typename T>
+template <typename T, int PM>
 __global__ void __launch_bounds__(FA_THREADS, 1)
     flash_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, T* __restrict__ out, int S, int heads) {
   extern __shared__ __align__(1024) unsigned char fa_smem_raw[];
@@ -259,8 +277,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           uint32_t pv[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c + 2 * i]), LOG2E, neg));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 2 * i + 1]), LOG2E, neg));
+            const float x0 = fmaf(__uint_as_float(sv[c + 2 * i]), LOG2E, neg);
+            const float x1 = fmaf(__uint_as_float(sv[c + 2 * i + 1]), LOG2E, neg);
+            const float p0 = (PM > 0 && ((2 * i) % (PM > 0 ? PM : 1)) == 0) ? ex2_poly(x0) : ex2_approx(x0);
+            const float p1 = (PM > 0 && ((2 * i + 1) % (PM > 0 ? PM : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1);
             ls[i & 3] += p0 + p1;
             pv[i] = pack_pair(p0, p1, T());
           }
@@ -309,11 +329,21 @@ void launch_attention_tc(edv::Launch& L, int dtype, const void* qkv, void* out, 
   uint64_t str[1] = {(uint64_t)3 * D * 2};
   uint32_t box[2] = {(uint32_t)FA_HD, (uint32_t)FA_BM};
   if (!make_map(L, &tm, dtype, qkv, 2, dims, str, box, 128)) return;
-  auto kern = flash_attention_tc_kernel<T>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // EDV_FA_POLY=<0|2|3|4>: every n-th exponential on the FMA pipe (tuning knob; 0 = all MUFU)
+  static int pm = -1;
+  if (pm < 0) {
+    const char* env = getenv("EDV_FA_POLY");
+    pm = env ? atoi(env) : FA_POLY_DEFAULT;
+    if (pm != 0 && pm != 2 && pm != 3 && pm != 4) pm = FA_POLY_DEFAULT;
+  }
+  void (*kern)(const CUtensorMap, T*, int, int) = pm == 0 ? flash_attention_tc_kernel<T, 0>
+                                                  : pm == 2 ? flash_attention_tc_kernel<T, 2>
+                                                  : pm == 3 ? flash_attention_tc_kernel<T, 3>
+                                                            : flash_attention_tc_kernel<T, 4>;
+  static bool attr_done[5] = {false, false, false, false, false};
+  if (!attr_done[pm]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM);
-    attr_done = true;
+    attr_done[pm] = true;
   }
   dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, F);
   kern<<<grid, FA_THREADS, FA_SMEM, L.stream>>>(tm, (T*)out, S, heads);

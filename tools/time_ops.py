@@ -1,0 +1,42 @@
+"""CUDA-event timing of single kernels at the BASELINE config-2 shapes (development aid).
+  python tools/time_ops.py attn [reps]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from endodav_b200 import engine as eng  # noqa: E402
+
+dt = torch.float16
+M = 32 * 1370
+g = torch.Generator().manual_seed(0)
+
+
+def rnd(*s, scale=1.0):
+    return (torch.randn(*s, generator=g) * scale).to(dt).cuda()
+
+
+def timeit(fn, reps=20):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+which = sys.argv[1]
+if which == "attn":
+    qkv = rnd(M, 1152, scale=0.5)
+    ref = None
+    us = timeit(lambda: eng.op_attention(qkv, 32, 1370, 6))
+    out = eng.op_attention(qkv, 32, 1370, 6).float()
+    t = qkv[:1370 * 2].float().reshape(2, 1370, 3, 6, 64).permute(2, 0, 3, 1, 4)
+    r = ((t[0] @ t[1].transpose(-1, -2)).softmax(-1) @ t[2]).transpose(1, 2).reshape(2 * 1370, 384)
+    print("attn EDV_FA_POLY=%s: %.1f us  (%.1f TFLOP/s)  max err vs fp32 %.3g" % (
+        os.environ.get("EDV_FA_POLY", "default"), us, 4 * 32 * 6 * 1370 * 1370 * 64 / us / 1e6, float((out[:2740] - r).abs().max())))
