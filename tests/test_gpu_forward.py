@@ -175,3 +175,43 @@ def test_full_size_clip_properties():
     assert bool(torch.isfinite(d0).all()) and float(d0.mean()) > 0.05 and float(d0.std()) > 1e-4
     again = model(x)[("disp", 0)]
     assert torch.equal(d0, again)
+
+
+def test_vitl_full_size_clip_runs():
+    """BASELINE config 4 shape family (ViT-L, 518 x 518, T=32; one clip): finite, non-degenerate, deterministic."""
+    ctor = dict(encoder="vitl", features=256, out_channels=[256, 512, 1024, 1024], r=4, lora_type="dvlora",
+                image_shape=(518, 518), disable_conv_head=True, residual_block_indexes=[])
+    model, cfg, sd = _build(ctor, 61, "fp16")
+    x = weights.make_frames(1, 32, 518, 518, 62).cuda()
+    d0 = model(x)[("disp", 0)]
+    assert tuple(d0.shape) == (32, 1, 518, 518)
+    assert bool(torch.isfinite(d0).all()) and float(d0.std()) > 1e-4
+    assert torch.equal(d0, model(x)[("disp", 0)])
+
+
+def test_clip_batch_sweep_matches_single_clips():
+    """BASELINE config 5 (Hamlyn-shaped clip batches at 256 x 320, network 224 x 280): a batch of B clips must
+    equal the B clips run one by one (no cross-clip leakage in the temporal modules), for T in {8, 16}."""
+    ctor = dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
+                image_shape=(224, 280), disable_conv_head=True, residual_block_indexes=[])
+    model, cfg, sd = _build(ctor, 1234, "fp16")
+    for T in (8, 16):
+        x = weights.make_frames(3, T, 256, 320, 70 + T).cuda()
+        full = model(x)[("disp", 0)].clone()
+        for b in range(3):
+            one = model(x[b:b + 1])[("disp", 0)]
+            assert torch.equal(full[b * T:(b + 1) * T], one), (T, b)
+
+
+def test_long_video_scared_shape():
+    """BASELINE config 3 shape (256 x 320 frames, network 224 x 280, 32-frame windows with stride 22):
+    4 windows; output shape / dtype, finiteness, and that the first window's frames are untouched by
+    the stitching (they are the raw network output resized to the frame size)."""
+    ctor = dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
+                image_shape=(224, 280), disable_conv_head=True, residual_block_indexes=[])
+    model, cfg, sd = _build(ctor, 1234, "fp16")
+    v = weights.make_video_u8(80, 256, 320, 9)
+    out = model.infer_video_depth(v)
+    assert out.shape == (80, 256, 320) and out.dtype == np.float32 and np.isfinite(out).all()
+    first = model.infer_video_depth(v[:32])
+    assert np.array_equal(out[:22], first[:22])
