@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -17,6 +18,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "conv_halo.cuh"
 #include "head_fused.cuh"
 
@@ -218,7 +220,60 @@ inline bool conv_halo_ok(const GemmArgs& a) {
          (a.e.act == ACT_NONE || a.e.act == ACT_RELU || a.e.act == ACT_SIGMOID) && a.e.map == MAP_LINEAR;
 }
 
+// 2-SM (cta_group::2) GEMM for the big token GEMMs (gemm_tc2.cuh)
+template <typename T, int BN> void launch_gemm_tc2(Launch& L, int dtype, const GemmArgs& a) {
+  using namespace tc;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.lda * 2};
+    uint32_t box[2] = {64u, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmA, dtype, a.A, 2, dims, str, box, 128)) return;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t str[1] = {(uint64_t)a.K * 2};
+    uint32_t box[2] = {64u, (uint32_t)(BN / 2)};
+    if (!make_tmap(L, &tmB, dtype, a.W, 2, dims, str, box, 128)) return;
+  }
+  const size_t stg_bytes = 16 * (size_t)GT_STG_WORDS * 4 + 16 * 128 * 4;
+  const int stage_bytes = gt2_stage_bytes<BN>();
+  int stages = (int)((220 * 1024 - stg_bytes - 2048) / stage_bytes);
+  if (stages > 8) stages = 8;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16 + stg_bytes;
+  auto kern = gemm_tc2_kernel<T, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    attr_done = true;
+  }
+  const int n_tiles = a.N / BN;
+  const long long total = (long long)((a.M + 255) / 256) * n_tiles;
+  int pairs = (int)std::min<long long>(total, num_sms() / 2);
+  note_gemm(L, a, 2);
+  kern<<<2 * pairs, GT_THREADS, smem, L.stream>>>(tmA, tmB, a.e, a.M, a.N, a.K, stages, n_tiles, (int)total);
+  L.check("gemm_tc2");
+}
+
+constexpr int GEMM_2SM_DEFAULT_MIN_M_DECL = 0;
+// EDV_GEMM_2SM=<min M> routes linear GEMMs with at least that many rows to the 2-SM kernel (0 = off)
+inline int gemm_2sm_min_m() {
+  static int v = -1;
+  if (v < 0) {
+    const char* env = getenv("EDV_GEMM_2SM");
+    v = env ? atoi(env) : GEMM_2SM_DEFAULT_MIN_M_DECL;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
+
 template <typename T> void launch_gemm_tc(Launch& L, int dtype, const GemmArgs& a) {
+  if (!a.conv && gemm_2sm_min_m() > 0 && a.M >= gemm_2sm_min_m() && a.K % 64 == 0 && a.lda == a.K && a.e.act != ACT_GEGLU &&
+      a.e.act != ACT_HEAD) {
+    if (a.N % 256 == 0) return launch_gemm_tc2<T, 256>(L, dtype, a);
+    if (a.N % 192 == 0) return launch_gemm_tc2<T, 192>(L, dtype, a);
+  }
   if (conv_halo_ok(a)) {
     if (a.N == 64) launch_conv_halo<T, 64>(L, a);
     else launch_conv_halo<T, 32>(L, a);

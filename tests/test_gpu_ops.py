@@ -227,3 +227,26 @@ def test_disp_head_fused(dtype, Fr, h, w, oh, ow, C, sig):
     ref = (F.relu(s) if sig == 0.0 else torch.sigmoid(sig * s)).float()
     err = (got - ref).abs()
     assert float(err.max()) <= 2e-3 * max(1.0, float(ref.abs().max())), float(err.max())
+
+
+def test_linear_2sm_kernel_matches_default():
+    """The experimental cta_group::2 GEMM (gemm_tc2.cuh, EDV_GEMM_2SM=<min M>) must agree bit for bit with
+    the default 1-SM kernel: same operands, same fp32 accumulation order per output element."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys; sys.path.insert(0, %r);"
+        "from endodav_b200 import engine as eng;"
+        "g = torch.Generator().manual_seed(3);"
+        "A = (torch.randn(20000, 384, generator=g)).half().cuda(); W = (torch.randn(1152, 384, generator=g) * 0.05).half().cuda();"
+        "b = torch.randn(1152, generator=g).cuda();"
+        "torch.save(eng.op_linear(A, W, b, 1).cpu(), sys.argv[1])" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for v in ("0", "512"):
+        path = "/tmp/edv_lin_%s.pt" % v
+        env = dict(os.environ, EDV_GEMM_2SM=v)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        outs.append(torch.load(path))
+    assert torch.equal(outs[0], outs[1])
