@@ -325,7 +325,15 @@ def main():
         else:
             roofline = dict(kernel=top["name"], bound="hbm", achieved=top["gbs"], peak=peaks["hbm_gbs"], unit="GB/s",
                             frac=top["gbs"] / peaks["hbm_gbs"])
-        roofline.update(traffic=None, share_of_step=top["share"], avg_launch_us=top["avg_us"], launches_per_step=top["count"] // K,
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_full_summary_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if top["name"] in tj:
+                traffic = tj[top["name"]]["bytes"]
+                traffic_src = "ncu --set full dram__bytes_read+write.sum of one launch at this shape (profiles/r1_ncu_full_summary.txt)"
+        roofline.update(traffic=traffic, traffic_source=traffic_src, share_of_step=top["share"], avg_launch_us=top["avg_us"], launches_per_step=top["count"] // K,
                         peak_source=peaks["source"] + (", sustained bf16" if top["bound"] == "tensor" else ""))
         # whole-forward tensor utilisation: all contraction FLOPs / step time
         roofline["step_tflops"] = sum(r["flops"] for r in table) / K / (ms / K * 1e-3) / 1e12

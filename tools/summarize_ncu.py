@@ -60,14 +60,33 @@ WANT = [
 ]
 
 
+OPS = ["fc1", "qkv", "fc2", "attn", "rcu", "tattn", "head", "oc", "ln"]   # tools/prof_ops.py order (--range mode)
+CALLSITE = {"fc1": "gemm_tc:blk.fc1", "qkv": "gemm_tc:blk.qkv", "fc2": "gemm_tc:blk.fc2", "attn": "flash_attention_tc",
+            "rcu": "conv_halo:ref.rcu.c1", "tattn": "temporal_attention", "head": "head_fused:oc2a", "oc": "conv_halo:oc1",
+            "ln": "layernorm"}
+
+
 def full(src, dst):
+    import json
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
+    ours = re.compile(r"gemm_tc|flash_attention|temporal_attention|head_fused|conv3x3_halo|layernorm_kernel|groupnorm|upsample_nhwc|preprocess_patches")
+    data = [d for d in data if ours.search(d[ki])]   # drop torch's own fill / RNG kernels from the captured range
+    # DRAM traffic per launch, keyed by bench.py's call-site names (one profiled launch per op, in OPS order)
+    traffic = {}
+    if len(data) == len(OPS):
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for op, d in zip(OPS, data):
+            traffic[CALLSITE[op]] = dict(bytes=float(d[ir].replace(",", "")) * mult[units[ir]] + float(d[iw].replace(",", "")) * mult[units[iw]],
+                                         kernel=short(d[ki]), shape_note="tools/prof_ops.py op '%s'" % op)
+        with open(dst.replace(".txt", "_traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     with open(dst, "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on ; source: %s\n" % src)
-        f.write("# every second launch of a kernel is the warm repetition (tools/prof_ops.py runs each op twice)\n")
+        f.write("# ncu --set full --clock-control none --profile-from-start off ; source: %s\n" % src)
+        f.write("# one warm launch per op of `tools/prof_ops.py --range` (ops in order: %s)\n" % " ".join(OPS))
         for d in data:
             f.write("\n== %s\n" % short(d[ki]))
             for w in WANT:
