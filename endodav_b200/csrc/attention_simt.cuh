@@ -180,22 +180,10 @@ __global__ void __launch_bounds__(ta_max_threads<HD>()) temporal_attention_kerne
     for (int j = 0; j < 32; ++j)
       if (j < Tn) mx = fmaxf(mx, s[j]);
     float l = 0.f;
-    if constexpr (sizeof(T) == 4) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        s[j] = (j < Tn) ? expf(s[j] - mx) : 0.f;
-        l += s[j];
-      }
-    } else {
-      // 16-bit paths: ex2.approx on log2(e)-scaled scores (2 instructions instead of expf's ~8)
-      const float nm = -mx * 1.4426950408889634f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float ev;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ev) : "f"(fmaf(s[j], 1.4426950408889634f, nm)));
-        s[j] = (j < Tn) ? ev : 0.f;
-        l += s[j];
-      }
+    for (int j = 0; j < 32; ++j) {
+      s[j] = (j < Tn) ? expf(s[j] - mx) : 0.f;
+      l += s[j];
     }
     const float inv = 1.f / l;
     float o[HD];
