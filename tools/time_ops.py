@@ -49,3 +49,18 @@ elif which in ("qkv", "fc1", "fc2", "proj"):
     ref = torch.nn.functional.gelu(ref) if act else ref
     print("%s EDV_GEMM_2SM=%s: %.1f us (%.0f TFLOP/s) max err %.3g" % (which, os.environ.get("EDV_GEMM_2SM", "0"), us,
                                                                       2.0 * M * N * K / us / 1e6, float((got - ref).abs().max())))
+elif which == "ln":
+    x = torch.randn(M, 384, generator=g).cuda()
+    gam, bet = torch.ones(384).cuda(), torch.zeros(384).cuda()
+    # rotate over 4 inputs so that successive launches do not find x in L2
+    xs = [x.clone() for _ in range(4)]
+    it = [0]
+
+    def f():
+        it[0] += 1
+        eng.op_layernorm(xs[it[0] & 3], gam, bet, 1e-6, dt)
+
+    us = timeit(f, 40)
+    got = eng.op_layernorm(x[:64], gam, bet, 1e-6, dt).float()
+    ref = torch.nn.functional.layer_norm(x[:64], (384,), gam, bet, 1e-6)
+    print("ln: %.1f us (%.0f GB/s incl. output alloc) max err %.3g" % (us, M * 384 * 6 / us / 1e3, float((got - ref).abs().max())))
