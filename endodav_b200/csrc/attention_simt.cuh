@@ -112,7 +112,7 @@ template <int HD> constexpr int ta_max_threads() { return HD >= 64 ? 256 : 512; 
 
 template <typename T, int HD>
 __global__ void __launch_bounds__(ta_max_threads<HD>()) temporal_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn, int hw, int C, int PB,
-                                          int HG) {
+                                          int HG, const float2* __restrict__ rope) {
   constexpr int VEC = 16 / (int)sizeof(T);       // elements per 16-byte chunk
   constexpr int QPAD = 16 / (int)sizeof(T);      // q rows are padded by 16 B: lanes (frames) read their own row
   extern __shared__ __align__(16) unsigned char tsm_raw[];
@@ -139,14 +139,30 @@ __global__ void __launch_bounds__(ta_max_threads<HD>()) temporal_attention_kerne
     const int pos = r % npos, f = r / npos;
     const T* src = qkv + ((long long)(b * Tn + f) * hw + d0 + pos) * ld + (long long)which * C + c0 + c * VEC;
     const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    const T* e = reinterpret_cast<const T*>(&raw);
+    float v[VEC];
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) v[u] = to_f<T>(e[u]);
+    if (rope && which < 2) {
+      // RoPE on q and k (pe='rope', motion_module/attention.py:403-429): channel pair i at frame f is
+      // rotated by the angle whose (cos, sin) sits in rope[f * C/2 + i]
+      const float2* rt = rope + (size_t)f * (C / 2) + (c0 + c * VEC) / 2;
+#pragma unroll
+      for (int u = 0; u < VEC; u += 2) {
+        const float2 cs = rt[u / 2];
+        const float a = v[u], bq = v[u + 1];
+        v[u] = a * cs.x - bq * cs.y;
+        v[u + 1] = a * cs.y + bq * cs.x;
+      }
+    }
     if (which == 0) {
-      *reinterpret_cast<uint4*>(Qs + (size_t)f * rowQ + pos * W + c * VEC) = raw;
+      T* dst = Qs + (size_t)f * rowQ + pos * W + c * VEC;
+      if (rope) store_vec<T, VEC>(dst, v);
+      else *reinterpret_cast<uint4*>(dst) = raw;
     } else {
       float* dst = (which == 1 ? Ks : Vs) + (size_t)f * rowKV + pos * W + c * VEC;
-      const T* e = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-      for (int u = 0; u < VEC; u += 4)
-        *reinterpret_cast<float4*>(dst + u) = make_float4(to_f<T>(e[u]), to_f<T>(e[u + 1]), to_f<T>(e[u + 2]), to_f<T>(e[u + 3]));
+      for (int u = 0; u < VEC; u += 4) *reinterpret_cast<float4*>(dst + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
     }
   }
   __syncthreads();

@@ -197,7 +197,7 @@ struct Fwd {
       layernorm(L, dt, hs, wf(an + "ln.w", C), wf(an + "ln.b", C), lnb, Mm, C, 1e-5f, 0, 0,
                 c->cfg.rope ? nullptr : wf(an + "pe", (size_t)T * C), hw, T);
       linear(lnb, Mm, C, an + "qkv.w", 3 * C, ep(qkvb, 3 * C, nullptr));
-      temporal_attention(L, dt, qkvb, att, B, T, hw, C);
+      temporal_attention(L, dt, qkvb, att, B, T, hw, C, c->cfg.rope ? wf(an + "rope", (size_t)T * C) : nullptr);
       {
         Epi e = ep(hs, C, wf(an + "out.b", C));
         e.out_f32 = 1; e.res1 = hs; e.res1_f32 = 1; e.ld_res1 = C;
@@ -539,7 +539,6 @@ int edv_create(const edv_config* cfg, edv_ctx** out) {
   if (cfg->num_frames < 1 || cfg->num_frames > 32)
     return set_err(nullptr, EDV_ERR_ARG, "edv_create: num_frames must be in [1,32]");
   if (cfg->dtype < EDV_F32 || cfg->dtype > EDV_F16) return set_err(nullptr, EDV_ERR_ARG, "edv_create: bad dtype");
-  if (cfg->rope) return set_err(nullptr, EDV_ERR_ARG, "edv_create: pe='rope' is not implemented yet");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();

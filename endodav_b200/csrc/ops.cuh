@@ -475,7 +475,7 @@ inline void head_fused(Launch& L, int dtype, const void* x, const void* w, const
 }
 
 template <typename T, int HD>
-void launch_temporal(Launch& L, const void* qkv, void* out, int B, int Tn, int hw, int C) {
+void launch_temporal(Launch& L, const void* qkv, void* out, int B, int Tn, int hw, int C, const float* rope) {
   const int heads = 8;
   // shared memory per (position, head): K and V in fp32, q/o in T
   const size_t per = (size_t)Tn * HD * (8 + sizeof(T));
@@ -496,18 +496,19 @@ void launch_temporal(Launch& L, const void* qkv, void* out, int B, int Tn, int h
   }
   dim3 grid((hw + pb - 1) / pb, B, heads / hg);
   L.note(4.0 * B * hw * heads * (double)Tn * Tn * HD, 4.0 * B * Tn * hw * C * sizeof(T));
-  kern<<<grid, 32 * hg * pb, smem, L.stream>>>((const T*)qkv, (T*)out, Tn, hw, C, pb, hg);
+  kern<<<grid, 32 * hg * pb, smem, L.stream>>>((const T*)qkv, (T*)out, Tn, hw, C, pb, hg, (const float2*)rope);
   L.check("temporal_attention");
 }
 
-inline void temporal_attention(Launch& L, int dtype, const void* qkv, void* out, int B, int Tn, int hw, int C) {
+inline void temporal_attention(Launch& L, int dtype, const void* qkv, void* out, int B, int Tn, int hw, int C,
+                               const float* rope = nullptr) {
   if (!L.ok()) return;
   if (Tn > 32 || Tn < 1) return L.fail(EDV_ERR_ARG, "temporal attention: T must be in [1,32] (motion_module.py:185-197)");
   if (C % 8 != 0) return L.fail(EDV_ERR_ARG, "temporal attention: C must be a multiple of 8");
   const int hd = C / 8;
 #define EDV_TA_CASE(HD_)                                                                   \
   if (hd == HD_) {                                                                         \
-    EDV_DISPATCH_T(dtype, { launch_temporal<T, HD_>(L, qkv, out, B, Tn, hw, C); });        \
+    EDV_DISPATCH_T(dtype, { launch_temporal<T, HD_>(L, qkv, out, B, Tn, hw, C, rope); });        \
     return;                                                                                \
   }
   EDV_TA_CASE(8)

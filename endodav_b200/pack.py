@@ -223,6 +223,12 @@ def pack_state_dict(sd, cfg, dtype=torch.bfloat16):
             if cfg.get("pe", "ape") == "ape":
                 pe = sd[ab + "pos_encoder.pe"].double()[0, :T]      # [T, C]
                 vec(an + "pe", pe)     # added to the LayerNorm output of frame f (motion_module.py:236-237)
+            else:
+                # RoPE over the full channel dim (motion_module/attention.py:403-429): pair i of q and k
+                # at frame t is rotated by t * theta^(-2i/C); table [T, C/2, (cos, sin)]
+                freqs = 1.0 / (10000.0 ** (torch.arange(0, C, 2, dtype=torch.float64)[: C // 2] / C))
+                ang = torch.outer(torch.arange(T, dtype=torch.float64), freqs)
+                vec(an + "rope", torch.stack([ang.cos(), ang.sin()], -1).reshape(T, C))
             mat(an + "out.w", sd[ab + "to_out.0.weight"])
             vec(an + "out.b", sd[ab + "to_out.0.bias"])
         vec(n + "ffln.w", sd[tb + "ff_norm.weight"])

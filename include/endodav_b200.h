@@ -58,7 +58,7 @@ typedef struct edv_config {
   int32_t out_sigmoid;     /* dpt_pyramid.py:98-102 */
   int32_t inv_sigmoid;     /* dpt_pyramid.py:105 */
   int32_t res_blocks;      /* bit i set: ViT block i has a ResBottleneckBlock (block.py:146-150) */
-  int32_t rope;            /* 0: sinusoidal APE table folded into the q|k|v bias; 1: RoPE */
+  int32_t rope;            /* 0: sinusoidal APE rows added by the LayerNorm that feeds q|k|v; 1: RoPE on q,k */
   int32_t dtype;           /* edv_dtype */
   int32_t engine;          /* edv_engine */
 } edv_config;

@@ -27,6 +27,10 @@ def _up(x_nhwc, oh, ow):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
+def frame_of_row(Fr, hw, T):
+    return (torch.arange(Fr * hw) // hw) % T
+
+
 def _pixshuf(y, Fr, ph, pw, k, cp):
     """GEMM output [F*ph*pw, k*k*cp] with columns (ky,kx,c) -> NHWC [F, k*ph, k*pw, cp]."""
     y = y.reshape(Fr, ph, pw, k, k, cp).permute(0, 1, 3, 2, 4, 5)
@@ -124,6 +128,14 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
                 frame = (torch.arange(Fr * hw) // hw) % T
                 ln = ln + pk[an + "pe"][frame]
             qkv = _lin(ln, pk[an + "qkv.w"])
+            if (an + "rope") in pk:
+                # rotate channel pairs of q and k by the frame's angle (table [T, C/2, (cos, sin)])
+                tab = pk[an + "rope"].reshape(-1, C // 2, 2)[frame_of_row(Fr, hw, T)]      # [rows, C/2, 2]
+                for w0 in (0, C):
+                    z = qkv[:, w0:w0 + C].reshape(-1, C // 2, 2)
+                    rot = torch.stack([z[..., 0] * tab[..., 0] - z[..., 1] * tab[..., 1],
+                                       z[..., 0] * tab[..., 1] + z[..., 1] * tab[..., 0]], -1).reshape(-1, C)
+                    qkv = torch.cat([qkv[:, :w0], rot, qkv[:, w0 + C:]], 1)
             q, k, v = qkv.reshape(B, T, hw, 3, 8, hd).permute(3, 0, 2, 4, 1, 5)  # [B,hw,8,T,hd]
             o = (q @ k.transpose(-1, -2)).softmax(-1) @ v
             o = o.permute(0, 3, 1, 2, 4).reshape(Fr * hw, C)

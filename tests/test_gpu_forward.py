@@ -53,7 +53,7 @@ def _metrics(pred, gt):
     return float(np.mean(np.abs(gt - pred) / gt)), float((thresh < 1.25).mean())
 
 
-FWD = [k for k, v in manifest().items() if v["kind"] == "forward" and v["ctor"].get("pe", "ape") == "ape"]
+FWD = [k for k, v in manifest().items() if v["kind"] == "forward"]   # includes the pe='rope' configuration
 
 
 @pytest.mark.parametrize("name", FWD)

@@ -61,7 +61,7 @@ def test_forward_without_gpu_fails_loudly():
 
 
 @pytest.mark.parametrize("name", ["fwd_vits_dvlora", "fwd_vits_b2", "fwd_vits_ssb_tlora", "fwd_vits_dash_tlora",
-                                  "fwd_vits_lora_res_convhead", "fwd_vitl"])
+                                  "fwd_vits_lora_res_convhead", "fwd_vits_rope", "fwd_vitl"])
 def test_packed_graph_matches_reference_golden(name):
     """pack.py + the engine's graph algebra reproduce the reference outputs (fp32, CPU emulation)."""
     m, arrays = load_case(name)
@@ -110,7 +110,7 @@ def test_pack_dtypes_and_alignment():
         pk = pack.pack_state_dict(sd, cfg, dt)
         for k, v in pk.items():
             assert v.is_contiguous()
-            if v.dim() == 2 and not k.endswith(".pe"):
+            if v.dim() == 2 and not k.endswith((".pe", ".rope")):
                 assert v.dtype == dt, k
                 assert v.shape[1] % 32 == 0, (k, v.shape)   # K of every GEMM is a multiple of 32
                 assert v.shape[0] % 32 == 0, (k, v.shape)   # N of every GEMM is a multiple of 32
