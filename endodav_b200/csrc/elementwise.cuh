@@ -64,6 +64,64 @@ __global__ void preprocess_patches_kernel(const void* __restrict__ src, T* __res
   store_vec<T, 8>(out + row * Kp + k0, val);
 }
 
+// ---------------------------------------------------------------------------------------
+// Host preprocessing of infer_video_depth moved to the GPU:
+//   frames[i].astype(float32) / 255 -> cv2.resize(INTER_CUBIC) -> HWC->CHW
+// (endodav.py:195; util/transform.py:109-113,139-158).  Restates OpenCV's float bicubic:
+// A = -0.75, half-pixel centres (fx = (dx + 0.5) * W/w - 0.5), border replicate, horizontal pass
+// then vertical pass, no anti-aliasing.  src uint8 [N,H,W,3] -> dst float32 [N,3,h,w].
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coeffs(float x, float* c) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+  c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+  c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+__global__ void cubic_resize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int N, int H, int W,
+                                       int h, int w) {
+  const long long total = (long long)N * h * w;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int dx = (int)(i % w);
+  const long long t = i / w;
+  const int dy = (int)(t % h);
+  const int n = (int)(t / h);
+  const double scale_x = (double)W / w, scale_y = (double)H / h;
+  // source coordinate in double, fraction rounded to float last (a float coordinate near 300 would lose
+  // 3e-5 of the fraction; OpenCV 4.x is accurate to 2e-7 against the exact cubic)
+  const double fxd = (dx + 0.5) * scale_x - 0.5, fyd = (dy + 0.5) * scale_y - 0.5;
+  const int sx = (int)floor(fxd), sy = (int)floor(fyd);
+  const float fx = (float)(fxd - sx), fy = (float)(fyd - sy);
+  float cx[4], cy[4];
+  cubic_coeffs(fx, cx);
+  cubic_coeffs(fy, cy);
+  int xs[4], ys[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    xs[k] = min(max(sx + k - 1, 0), W - 1);
+    ys[k] = min(max(sy + k - 1, 0), H - 1);
+  }
+  const uint8_t* base = src + (size_t)n * H * W * 3;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint8_t* row = base + (size_t)ys[r] * W * 3;
+    float hs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint8_t* px = row + xs[k] * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hs[c] += ((float)px[c] / 255.0f) * cx[k];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += hs[c] * cy[r];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dst[(((size_t)n * 3 + c) * h + dy) * w + dx] = acc[c];
+}
+
 // cls row of every frame: x[f, 0, :] = cls_token + pos_embed[0]  (vision_transformer.py:225-227)
 __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ cls_row, int F, int N, int D) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

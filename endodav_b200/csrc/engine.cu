@@ -884,6 +884,17 @@ int edv_op_disp_head(int dtype, const void* X, const void* Wt, const float* bias
   return finish(L);
 }
 
+int edv_op_cubic_resize_u8(const uint8_t* src, float* dst, int N, int H, int W, int h, int w, void* stream) {
+  if (!src || !dst || N < 1 || H < 1 || W < 1 || h < 1 || w < 1) return EDV_ERR_ARG;
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  const long long total = (long long)N * h * w;
+  L.note(0, (double)N * H * W * 3 + (double)total * 12);
+  cubic_resize_u8_kernel<<<nblk(total, 256), 256, 0, L.stream>>>(src, dst, N, H, W, h, w);
+  L.check("cubic_resize_u8");
+  return finish(L);
+}
+
 int edv_op_layernorm(int dtype, const float* X, const float* gamma, const float* beta, void* Y, int M, int D,
                      float eps, void* stream) {
   Launch L;

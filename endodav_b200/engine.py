@@ -21,7 +21,7 @@ EXPORTS = [
     "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_op_linear", "edv_op_conv3x3",
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
     "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
-    "edv_op_disp_head",
+    "edv_op_disp_head", "edv_op_cubic_resize_u8",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library():
     lib.edv_op_attention.argtypes = [ci, ci, vp, vp, ci, ci, ci, vp]
     lib.edv_op_temporal_attention.argtypes = [ci, vp, vp, ci, ci, ci, ci, vp]
     lib.edv_op_disp_head.argtypes = [ci, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, vp]
+    lib.edv_op_cubic_resize_u8.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     lib.edv_op_layernorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ctypes.c_float, vp]
     lib.edv_op_groupnorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
     lib.edv_op_upsample.argtypes = [ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
@@ -259,6 +260,15 @@ def op_disp_head(X, Wt, bias, head_w, oh, ow, sig_sign=0.0):
     out = torch.empty(F, oh, ow, dtype=torch.float32, device=X.device)
     _check(lib.edv_op_disp_head(_dt(X), _ptr(X), _ptr(Wt), _ptr(bias), _ptr(head_w), _ptr(out), F, H1, W1, oh, ow, Cin,
                                 ctypes.c_float(sig_sign), _stream()), None, "edv_op_disp_head")
+    return out
+
+
+def op_cubic_resize_u8(frames_u8, h, w):
+    """uint8 [N,H,W,3] (device) -> float32 [N,3,h,w]: the reference's per-frame cv2 cubic resize of frame/255."""
+    lib = load_library()
+    N, H, W, _ = frames_u8.shape
+    out = torch.empty(N, 3, h, w, dtype=torch.float32, device=frames_u8.device)
+    _check(lib.edv_op_cubic_resize_u8(_ptr(frames_u8), _ptr(out), N, H, W, h, w, _stream()), None, "edv_op_cubic_resize_u8")
     return out
 
 

@@ -149,7 +149,7 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
     ``forward_window(clip[1,32,3,h,w] float32 tensor, (H,W)) -> [32,H,W] float32 tensor`` can be
     injected by tests (index/stitch logic on CPU); by default it is the model's CUDA engine
     with the final resize fused into the same launch sequence."""
-    frames = np.asarray(frames)
+    frames = np.ascontiguousarray(frames)
     if frames.ndim != 4 or frames.shape[-1] != 3:
         raise ValueError("frames must be [N,H,W,3], got %s" % (frames.shape,))
     n, H, W = frames.shape[:3]
@@ -169,25 +169,75 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         if next(model.parameters()).device != dev:
             model.to(dev)
         eng = model._ensure_engine(ih // 14, iw // 14)
-        # two pinned staging buffers: the host fills window j+1 while the GPU runs window j
-        pinned = [torch.empty(1, INFER_LEN, 3, new_h, new_w, dtype=torch.float32).pin_memory() for _ in range(2)]
+        import os
+
+        from . import engine as _engine
+
+        gpu_pre = os.environ.get("ENDODAV_PREPROCESS", "gpu").lower() != "host"
+        # two pinned staging buffers: the host fills window j+1 while the GPU runs window j.
+        # gpu_pre (default): the raw uint8 frames of the window are uploaded (4x fewer bytes than the
+        # resized float clip) and the reference's /255 + cv2 INTER_CUBIC resize + HWC->CHW runs in a
+        # CUDA kernel (edv_op_cubic_resize_u8); ENDODAV_PREPROCESS=host keeps the reference's host path.
+        if gpu_pre:
+            pinned = [torch.empty(INFER_LEN, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        else:
+            pinned = [torch.empty(1, INFER_LEN, 3, new_h, new_w, dtype=torch.float32).pin_memory() for _ in range(2)]
         copied = [None, None]
+
+        def launch(j):
+            """enqueue window mine[j]: H2D of its frames, (cubic resize,) forward, resize back -> device tensor"""
+            slot = j & 1
+            if copied[slot] is not None:
+                copied[slot].synchronize()  # the earlier H2D copy out of this buffer has finished
+            buf = pinned[slot]
+            idx = window_frame_indices(mine[j], n)
+            if gpu_pre:
+                np.take(frames, idx, axis=0, out=buf.numpy())
+                xu8 = buf.to(dev, non_blocking=True)
+            else:
+                for i, src in enumerate(idx):
+                    buf[0, i].copy_(torch.from_numpy(cache.get(int(src))))
+                x = buf.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            copied[slot] = ev
+            if gpu_pre:
+                x = _engine.op_cubic_resize_u8(xu8, new_h, new_w).view(1, INFER_LEN, 3, new_h, new_w)
+            return eng.forward(x, resize_to=(H, W), want_pyramid=False)[1]
+
+        if world == 1:
+            # Single GPU: stream the windows.  Window j+2 is enqueued before window j is handed to the
+            # (strictly sequential, host-side) stitching, and every result comes back through a small
+            # ring of pinned buffers, so GPU work, D2H copies and the numpy stitching overlap.
+            AHEAD, RING = 2, 3
+            ring = [torch.empty(INFER_LEN, H, W, dtype=torch.float32).pin_memory() for _ in range(RING)]
+            done = [None] * RING
+
+            def stream():
+                with torch.cuda.device(dev):
+                    eng.plan(1, INFER_LEN, new_h, new_w, ih, iw)
+
+                    def enqueue(j):
+                        ring[j % RING].copy_(launch(j), non_blocking=True)
+                        done[j % RING] = torch.cuda.Event()
+                        done[j % RING].record()
+
+                    for j in range(min(AHEAD, len(mine))):
+                        enqueue(j)
+                    for j in range(len(mine)):
+                        if j + AHEAD < len(mine):
+                            enqueue(j + AHEAD)   # reuses the slot of window j-1, which the consumer has finished with
+                        done[j % RING].synchronize()
+                        arr = ring[j % RING].numpy()
+                        yield arr.copy() if j == 0 else arr   # window 0's frames are kept by reference in the output list
+
+            return stitch_windows(stream(), n)
+
         local = []
         with torch.cuda.device(dev):
             eng.plan(1, INFER_LEN, new_h, new_w, ih, iw)
-            for j, k in enumerate(mine):
-                slot = j & 1
-                if copied[slot] is not None:
-                    copied[slot].synchronize()  # the earlier H2D copy out of this buffer has finished
-                buf = pinned[slot]
-                for i, src in enumerate(window_frame_indices(k, n)):
-                    buf[0, i].copy_(torch.from_numpy(cache.get(int(src))))
-                x = buf.to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
-                copied[slot] = ev
-                _, resized = eng.forward(x, resize_to=(H, W), want_pyramid=False)
-                local.append(resized)
+            for j in range(len(mine)):
+                local.append(launch(j))
         local_t = torch.stack(local, 0) if local else torch.empty(0, INFER_LEN, H, W, dtype=torch.float32, device=dev)
     else:
         local = []

@@ -149,6 +149,11 @@ int edv_op_temporal_attention(int dtype, const void* qkv, void* out, int B, int 
 int edv_op_disp_head(int dtype, const void* X, const void* Wt, const float* bias, const float* head_w, float* out, int F,
                      int H1, int W1, int OH, int OW, int Cin, float sig_sign, void* stream);
 
+/* Host preprocessing of infer_video_depth on the GPU: uint8 RGB frames [N,H,W,3] -> float32 [N,3,h,w] =
+ * cv2.resize(frame / 255, (w,h), INTER_CUBIC) in CHW order (OpenCV's float bicubic: A=-0.75, half-pixel
+ * centres, replicated border).  Replaces endodav.py:195 + util/transform.py:109-113,139-158. */
+int edv_op_cubic_resize_u8(const uint8_t* src, float* dst, int N, int H, int W, int h, int w, void* stream);
+
 /* LayerNorm over the last dim: X[M,D] float32 -> Y[M,D] `dtype`. */
 int edv_op_layernorm(int dtype, const float* X, const float* gamma, const float* beta, void* Y, int M, int D,
                      float eps, void* stream);

@@ -215,3 +215,16 @@ def test_long_video_scared_shape():
     assert out.shape == (80, 256, 320) and out.dtype == np.float32 and np.isfinite(out).all()
     first = model.infer_video_depth(v[:32])
     assert np.array_equal(out[:22], first[:22])
+
+
+def test_gpu_preprocessing_equals_host_preprocessing(monkeypatch):
+    """the driver's default GPU cubic resize must reproduce the reference's host
+    (cv2) preprocessing path end to end."""
+    m, arrays = load_case("video_n45")
+    model, cfg, sd = _build(m["ctor"], m["weight_seed"], "fp32")
+    N, H, W = m["input"]
+    v = weights.make_video_u8(N, H, W, m["frame_seed"])
+    a = model.infer_video_depth(v)
+    monkeypatch.setenv("ENDODAV_PREPROCESS", "host")
+    b = model.infer_video_depth(v)
+    assert float(np.abs(a - b).max()) <= 1e-4 * max(1.0, float(np.abs(b).max()))
