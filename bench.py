@@ -160,7 +160,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vits_518_t32", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"])
-    ap.add_argument("--cpu-frames", type=int, default=4, help="frames per step of the CPU baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=16, help="frames per step of the CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the CPU baseline sample in the GPU arm (~10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels-out", default=None, help="write the per-call-site kernel table (JSON) here")
     args = ap.parse_args()
@@ -355,7 +356,7 @@ def main():
 
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_reference_fps(ctor, (B, T, H, Wd), args.cpu_frames, 1, 1)
+        cpu_base, _ = cpu_reference_fps(ctor, (B, T, H, Wd), args.cpu_frames, max(1, args.cpu_steps), 1)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
