@@ -11,7 +11,7 @@
 // ---------------------------------------------------------------------------------------
 template <typename T, bool U8>
 __global__ void preprocess_patches_kernel(const void* __restrict__ src, T* __restrict__ out, int F, int H, int W,
-                                          int h, int w, int Kp) {
+                                          int h, int w, int Kp, int normalize) {
   // one thread = 8 consecutive k of one patch row (one aligned 16-byte store for 16-bit T)
   const int ph = h / 14, pw = w / 14;
   const int kch = Kp / 8;
@@ -56,7 +56,7 @@ __global__ void preprocess_patches_kernel(const void* __restrict__ src, T* __res
       }
       const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
       const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-      o = (v - mean) / stdv;
+      o = normalize ? (v - mean) / stdv : v;
     }
     val[j] = o;
     if (++kx == 14) { kx = 0; if (++ky == 14) { ky = 0; ++c; } }

@@ -323,8 +323,9 @@ struct Fwd {
       unsigned blocks = nblk(tot / 8, 256);
       L.note(0, (double)p.BT * 3 * p.H * p.W * (u8 ? 1 : 4) + (double)tot * es);
       EDV_DISPATCH_T(dt, {
-        if (u8) preprocess_patches_kernel<T, true><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH);
-        else preprocess_patches_kernel<T, false><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH);
+        const int nrm = g.no_normalize ? 0 : 1;  // endodac with pre_norm=False feeds raw [0,1] pixels (endodac.py:208-211)
+        if (u8) preprocess_patches_kernel<T, true><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH, nrm);
+        else preprocess_patches_kernel<T, false><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH, nrm);
       });
       L.check("preprocess");
       const float* cls = wf("cls_row", D);
@@ -421,10 +422,14 @@ struct Fwd {
     snapshot("layer2", L2, false, (long long)p.BT * 4 * p.P, p.Cp[1], g.out_channels[1]);
     snapshot("layer3", L3, false, p.Mp, p.Cp[2], g.out_channels[2]);
     snapshot("layer4", L4, false, (long long)p.BT * p.ph2 * p.pw2, p.Cp[3], g.out_channels[3]);
-    void* L3m = buf("L3m");
-    void* L4m = buf("L4m");
-    motion(0, L3, L3m);
-    motion(1, L4, L4m);
+    // endodac (models/endodac/endodac.py:93-127) is this head without the four temporal modules
+    const bool mm_on = !g.no_motion;
+    void* L3m = mm_on ? buf("L3m") : L3;
+    void* L4m = mm_on ? buf("L4m") : L4;
+    if (mm_on) {
+      motion(0, L3, L3m);
+      motion(1, L4, L4m);
+    }
     snapshot("mm0", L3m, false, p.Mp, p.Cp[2], g.out_channels[2]);
     snapshot("mm1", L4m, false, (long long)p.BT * p.ph2 * p.pw2, p.Cp[3], g.out_channels[3]);
     // scratch.layer{1-4}_rn (3x3, no bias) -> F channels, plus relu copies for the RCUs
@@ -440,12 +445,13 @@ struct Fwd {
       e = ep(l4r, F_, nullptr); e.out_relu = l4rr;
       conv3(L4m, p.BT, p.ph2, p.pw2, p.Cp[3], "rn4.w", F_, e);
     }
-    void *p4 = buf("p4"), *p4m = buf("p4m"), *p3 = buf("p3"), *p3m = buf("p3m"), *p2 = buf("p2"), *p1 = buf("p1");
+    void *p4 = buf("p4"), *p3 = buf("p3"), *p2 = buf("p2"), *p1 = buf("p1");
+    void *p4m = mm_on ? buf("p4m") : p4, *p3m = mm_on ? buf("p3m") : p3;
     fusion(4, l4r, l4rr, nullptr, nullptr, p.ph2, p.pw2, p.ph, p.pw, p4);
     snapshot("path4_pre", p4, false, p.Mp, F_, F_);
-    motion(2, p4, p4m);
+    if (mm_on) motion(2, p4, p4m);
     fusion(3, p4m, nullptr, l3r, l3rr, p.ph, p.pw, 2 * p.ph, 2 * p.pw, p3);
-    motion(3, p3, p3m);
+    if (mm_on) motion(3, p3, p3m);
     snapshot("path3", p3m, false, (long long)p.BT * 4 * p.P, F_, F_);
     fusion(2, p3m, nullptr, l2r, l2rr, 2 * p.ph, 2 * p.pw, 4 * p.ph, 4 * p.pw, p2);
     fusion(1, p2, nullptr, l1r, l1rr, 4 * p.ph, 4 * p.pw, 8 * p.ph, 8 * p.pw, p1);
@@ -597,7 +603,7 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
   p.mm[1] = MMPlan{p.Cp[3], p.ph2, p.pw2};
   p.mm[2] = MMPlan{F_, p.ph, p.pw};
   p.mm[3] = MMPlan{F_, 2 * p.ph, 2 * p.pw};
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 4 && !g.no_motion; ++j) {
     int hd = p.mm[j].C / 8;
     if (!(hd == 8 || hd == 24 || hd == 32 || hd == 48 || hd == 128))
       return set_err(ctx, EDV_ERR_ARG, "edv_plan: temporal head dim %d unsupported (8,24,32,48,128)", hd);
@@ -650,8 +656,10 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
   add("L4p", px3 * p.Cp[3] * es);
   add("L4", px4 * p.Cp[3] * es);
   add("col", px4 * 9 * p.Cp[3] * es);
-  add("L3m", px3 * p.Cp[2] * es);
-  add("L4m", px4 * p.Cp[3] * es);
+  if (!g.no_motion) {
+    add("L3m", px3 * p.Cp[2] * es);
+    add("L4m", px4 * p.Cp[3] * es);
+  }
   // motion-module scratch, sized for the largest of the four modules
   size_t mmC = 0, mm3 = 0, mm4 = 0, mm8 = 0;
   for (int j = 0; j < 4; ++j) {
@@ -661,16 +669,18 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
     mm4 = std::max(mm4, rows * 4 * C);
     mm8 = std::max(mm8, rows * 8 * C);
   }
-  add("mm.stats", (size_t)p.BT * 32 * (1 + GN_MAX_SPLIT) * sizeof(float2));
-  add("mm.gn", mmC * es);
-  add("mm.hs", mmC * 4);
-  add("mm.ln", mmC * es);
-  add("mm.qkv", mm3 * es);
-  add("mm.att", mmC * es);
-  add("mm.gg", mm4 * es);
-  add("mm.hsT", mmC * es);
+  if (!g.no_motion) {
+    add("mm.stats", (size_t)p.BT * 32 * (1 + GN_MAX_SPLIT) * sizeof(float2));
+    add("mm.gn", mmC * es);
+    add("mm.hs", mmC * 4);
+    add("mm.ln", mmC * es);
+    add("mm.qkv", mm3 * es);
+    add("mm.att", mmC * es);
+    add("mm.gg", mm4 * es);
+    add("mm.hsT", mmC * es);
+  }
   const bool simt = (g.dtype == EDV_F32) || g.engine == EDV_ENGINE_SIMT;
-  if (simt) add("mm.gg2", mm8 * es);
+  if (simt && !g.no_motion) add("mm.gg2", mm8 * es);
   add("l1r", px1 * F_ * es); add("l1rr", px1 * F_ * es);
   add("l2r", px2 * F_ * es); add("l2rr", px2 * F_ * es);
   add("l3r", px3 * F_ * es); add("l3rr", px3 * F_ * es);

@@ -31,6 +31,7 @@ class EdvConfig(ctypes.Structure):
         ("features", ctypes.c_int32), ("out_channels", ctypes.c_int32 * 4), ("num_frames", ctypes.c_int32),
         ("conv_head", ctypes.c_int32), ("out_sigmoid", ctypes.c_int32), ("inv_sigmoid", ctypes.c_int32),
         ("res_blocks", ctypes.c_int32), ("rope", ctypes.c_int32), ("dtype", ctypes.c_int32), ("engine", ctypes.c_int32),
+        ("no_motion", ctypes.c_int32), ("no_normalize", ctypes.c_int32),
     ]
 
 

@@ -29,6 +29,8 @@ from . import video as _video
 _MODEL_SIZES = {
     "vits": dict(dim=384, depth=12, heads=6, pos_tokens=37 * 37 + 1, taps=[2, 5, 8, 11]),
     "vitl": dict(dim=1024, depth=24, heads=16, pos_tokens=16 * 16 + 1, taps=[4, 11, 17, 23]),
+    # endodac "base" (vision_transformer.py:368-382; endodac.py:176-199)
+    "vitb": dict(dim=768, depth=12, heads=12, pos_tokens=37 * 37 + 1, taps=[8, 9, 10, 11]),
 }
 
 
@@ -50,9 +52,11 @@ def _lora_entries(prefix, n_in, n_out, lora_type, r):
 
 
 def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_type, residual_block_indexes,
-                     temporal_lora, disable_conv_head):
+                     temporal_lora, disable_conv_head, motion=True, head_prefix="head."):
     """Ordered ``[(state_dict key, shape, init kind)]`` reproducing the reference's checkpoint
-    layout.  ``init kind`` is only used for fresh random models."""
+    layout.  ``init kind`` is only used for fresh random models.
+    ``motion=False, head_prefix="depth_head."`` is the layout of the ``endodac`` image model
+    (models/endodac/endodac.py:14-127,213-216): the same DPT head without temporal modules."""
     sz = _MODEL_SIZES[encoder]
     D, F, oc = sz["dim"], features, list(out_channels)
     L = []
@@ -78,7 +82,7 @@ def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_ty
                   (rb + "conv3.weight", (D, bc, 1, 1), "kaiming"), (rb + "norm3.weight", (D,), "zeros"),
                   (rb + "norm3.bias", (D,), "zeros")]
     L += [(p + "norm.weight", (D,), "ones"), (p + "norm.bias", (D,), "zeros")]
-    h = "head."
+    h = head_prefix
     for i in range(4):
         L += [(h + "projects.%d.weight" % i, (oc[i], D, 1, 1), "kaiming"), (h + "projects.%d.bias" % i, (oc[i],), "zeros")]
     L += [(h + "resize_layers.0.weight", (oc[0], oc[0], 4, 4), "kaiming"), (h + "resize_layers.0.bias", (oc[0],), "zeros"),
@@ -98,7 +102,7 @@ def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_ty
         L += [(s + "output_conv1.weight", (F // 2, F, 3, 3), "kaiming"), (s + "output_conv1.bias", (F // 2,), "zeros"),
               (s + "output_conv2.0.weight", (32, F // 2, 3, 3), "kaiming"), (s + "output_conv2.0.bias", (32,), "zeros"),
               (s + "output_conv2.2.weight", (1, 32, 1, 1), "kaiming"), (s + "output_conv2.2.bias", (1,), "zeros")]
-    for j, C in enumerate([oc[2], oc[3], F, F]):
+    for j, C in enumerate([oc[2], oc[3], F, F] if motion else []):
         t = h + "motion_modules.%d.temporal_transformer." % j
         L += [(t + "norm.weight", (C,), "ones"), (t + "norm.bias", (C,), "zeros"),
               (t + "proj_in.weight", (C, C), "kaiming"), (t + "proj_in.bias", (C,), "zeros")]
@@ -265,7 +269,7 @@ class endodav(nn.Module):
         c = _engine.EdvConfig()
         c.dim, c.depth, c.heads = sz["dim"], sz["depth"], sz["heads"]
         for i in range(4):
-            c.taps[i] = sz["taps"][i]
+            c.taps[i] = (self._cfg.get("taps") or sz["taps"])[i]
             c.out_channels[i] = self._cfg["out_channels"][i]
         c.features = self._cfg["features"]
         c.num_frames = self._cfg["num_frames"]
@@ -279,7 +283,13 @@ class endodav(nn.Module):
         c.rope = 1 if self._cfg["pe"] == "rope" else 0
         c.dtype = _engine.DTYPES[self._dtype_name]
         c.engine = self._engine_kind
+        c.no_motion = 0 if self._cfg.get("motion", True) else 1
+        c.no_normalize = 0 if getattr(self, "_normalize", True) else 1
         return c
+
+    def _pack_state_dict(self):
+        """state_dict under the key names pack.py reads (the endodav layout)."""
+        return self.state_dict()
 
     def _versions(self):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
@@ -298,13 +308,13 @@ class endodav(nn.Module):
             self._pos_key = None
         ver = self._versions()
         if ver != self._packed_versions:
-            sd = self.state_dict()
+            sd = self._pack_state_dict()
             tdt = _engine.TORCH_DTYPE[_engine.DTYPES[self._dtype_name]]
             self._eng.set_weights(_pack.pack_state_dict(sd, self._cfg, tdt))
             self._packed_versions = ver
             self._pos_key = None
         if self._pos_key != (ph, pw):
-            self._eng.set_weights(_pack.pos_tables(self.state_dict(), self._cfg, ph, pw))
+            self._eng.set_weights(_pack.pos_tables(self._pack_state_dict(), self._cfg, ph, pw))
             self._pos_key = (ph, pw)
         return self._eng
 
@@ -341,3 +351,129 @@ class endodav(nn.Module):
         """endodav.infer_video_depth (endodav.py:162-254).  ``input_size`` is ignored exactly as in
         the reference (:164-174).  Uses every visible rank when torch.distributed is initialised."""
         return _video.infer_video_depth(self, frames, device=device)
+
+
+class endodac(endodav):
+    """Drop-in for the reference's image model ``endodac`` (models/endodac/endodac.py:144-272):
+    the same DINOv2 encoder (+ LoRA / DV-LoRA MLP adapters) and DPT head as ``endodav`` without the
+    temporal modules, checkpoint keys under ``pretrained.*`` / ``depth_head.*``.  It runs on the
+    same sm_100a engine (``edv_config.no_motion``); SURVEY.md section 8(f) row 2.
+
+    Kept from the reference: constructor keywords and defaults (:153-165), the size tables
+    (:171-199), ``forward(pixel_values[B,3,H,W] or [B,T,3,H,W]) -> {("disp", s)}`` (:246-259) and
+    ``infer_video_depth(frames, batch_size=8)`` (:261-272)."""
+
+    _SIZES = {  # endodac.py:171-199
+        "small": dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384]),
+        "base": dict(encoder="vitb", features=128, out_channels=[96, 192, 384, 768]),
+    }
+
+    def __init__(
+        self,
+        backbone_size="base",
+        r=4,
+        image_shape=(224, 280),
+        lora_type="lora",
+        pretrained_path=None,
+        residual_block_indexes=[],
+        include_cls_token=True,
+        use_cls_token=False,
+        use_bn=False,
+        pre_norm=False,
+        inv_sigmoid=False,
+        disable_conv_head=False,
+        dtype=None,
+    ):
+        nn.Module.__init__(self)
+        assert r > 0                                       # endodac.py:168
+        if backbone_size not in self._SIZES:
+            raise KeyError(backbone_size)                  # the reference indexes its tables the same way (:200-204)
+        if use_bn:
+            raise NotImplementedError("use_bn=True is not used by any reference script and is not built")
+        if use_cls_token:
+            raise NotImplementedError("use_cls_token=True (readout projects) is not built")
+        if not include_cls_token:
+            raise NotImplementedError("include_cls_token=False is not built")
+        if lora_type not in ("none", "lora", "dvlora"):
+            # endodac.py:213-224 installs adapters only for these; any other string leaves plain linears
+            lora_type = "none"
+        sz = self._SIZES[backbone_size]
+        self.backbone_size = backbone_size
+        self.encoder = sz["encoder"]
+        self.embedding_dim = _MODEL_SIZES[self.encoder]["dim"]
+        self.image_shape = tuple(image_shape)
+        self.r = r
+        self._cfg = dict(encoder=self.encoder, features=sz["features"], out_channels=list(sz["out_channels"]),
+                         num_frames=32, pe="ape", r=r, lora_type=lora_type,
+                         residual_block_indexes=list(residual_block_indexes), temporal_lora=False,
+                         disable_conv_head=disable_conv_head, motion=False)
+        # forward taps get_intermediate_layers(x, 4): the LAST four blocks (endodac.py:254;
+        # vision_transformer.py:292-293), not the [2,5,8,11] table at endodac.py:183-186
+        depth = _MODEL_SIZES[self.encoder]["depth"]
+        self._cfg["taps"] = list(range(depth - 4, depth))
+        # LoraLinear(..., r=r) keeps lora_alpha=1 here: scaling 1/r, not endodav's 2 (endodac.py:222-223)
+        self._cfg["lora_scale"] = 1.0 / r
+        self._normalize = bool(pre_norm)                   # endodac.py:208-211: identity unless pre_norm
+        self._inv_sigmoid = bool(inv_sigmoid)
+        self._out_sigmoid = False
+        self._dtype_name = (dtype or os.environ.get("ENDODAV_DTYPE", "fp16")).lower()
+        if self._dtype_name not in _engine.DTYPES:
+            raise ValueError("dtype must be one of %s" % sorted(_engine.DTYPES))
+        self._engine_kind = {"tc": _engine.ENGINE_TC, "simt": _engine.ENGINE_SIMT}[os.environ.get("ENDODAV_ENGINE", "tc").lower()]
+        for key, shape, kind in parameter_layout(head_prefix="depth_head.", **{k: v for k, v in self._cfg.items() if k not in ("taps", "lora_scale")}):
+            _attach(self, key, _init_tensor(shape, kind), False)
+        _listify(self)
+        self._eng = None
+        self._packed_versions = None
+        self._pos_key = None
+        if pretrained_path is not None:
+            arch = {"small": "v2_vits", "base": "v2_vitb"}[backbone_size]   # endodac.py:177-182
+            path = os.path.join(pretrained_path, "depth_anything_{}.pth".format(arch))
+            self.load_state_dict(torch.load(path, map_location="cpu"), strict=False)
+            print("load pretrained weight from {}\n".format(path))
+
+    def _pack_state_dict(self):
+        return {("head." + k[len("depth_head."):] if k.startswith("depth_head.") else k): v
+                for k, v in self.state_dict().items()}
+
+    @torch.no_grad()
+    def forward(self, pixel_values):
+        """endodac.forward (endodac.py:246-259): [B,3,H,W] (or [B,T,3,H,W], flattened) in [0,1] ->
+        {("disp", s): [B,1,h_s,w_s]}."""
+        if pixel_values.dim() == 5:
+            pixel_values = pixel_values.flatten(0, 1)
+        if pixel_values.dim() != 4 or pixel_values.shape[1] != 3:
+            raise ValueError("expected [B,3,H,W], got %s" % (tuple(pixel_values.shape),))
+        Bn, _, H, W = pixel_values.shape
+        h, w = self.image_shape
+        assert h % 14 == 0, f"Input image height {h} is not a multiple of patch height 14"
+        assert w % 14 == 0, f"Input image width {w} is not a multiple of patch width: 14"
+        eng = self._ensure_engine(h // 14, w // 14)
+        x = pixel_values.to(device=eng.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(eng.device):
+            eng.plan(Bn, 1, H, W, h, w)
+            disp, _ = eng.forward(x)
+        return {("disp", s): disp[s] for s in range(4)}
+
+    @torch.no_grad()
+    def infer_video_depth(self, frames, batch_size=8, device='cuda'):
+        """endodac.infer_video_depth (endodac.py:261-272): independent chunks of ``batch_size`` frames,
+        each resized back to the frame size (bilinear, align_corners=True).  The uint8 -> float32/255
+        CHW conversion and the final resize run in the library's kernels."""
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim != 4 or frames.shape[-1] != 3 or frames.dtype != np.uint8:
+            raise ValueError("frames must be uint8 [N,H,W,3]")
+        N, H, W, _ = frames.shape
+        h, w = self.image_shape
+        eng = self._ensure_engine(h // 14, w // 14)
+        out = np.empty((N, H, W), dtype=np.float32)
+        with torch.cuda.device(eng.device):
+            for c0 in range(0, N, batch_size):
+                chunk = torch.from_numpy(frames[c0:c0 + batch_size]).to(eng.device)
+                n = chunk.shape[0]
+                # identity-size bicubic is exact (taps 0,1,0,0): this is frame.astype(float32)/255 in CHW
+                x = _engine.op_cubic_resize_u8(chunk, H, W)
+                eng.plan(n, 1, H, W, h, w)
+                _, resized = eng.forward(x, resize_to=(H, W), want_pyramid=False)
+                out[c0:c0 + n] = resized.cpu().numpy()
+        return out

@@ -25,6 +25,7 @@ import torch
 ENCODERS = {
     "vits": dict(dim=384, depth=12, heads=6, taps=[2, 5, 8, 11]),
     "vitl": dict(dim=1024, depth=24, heads=16, taps=[4, 11, 17, 23]),
+    "vitb": dict(dim=768, depth=12, heads=12, taps=[2, 5, 8, 11]),   # endodac "base"
 }
 KPATCH = 640
 
@@ -33,7 +34,7 @@ def round_up(v, m):
     return (v + m - 1) // m * m
 
 
-def merged_linear_weight(sd, prefix, lora_type):
+def merged_linear_weight(sd, prefix, lora_type, lora_scale=2.0):
     w = sd[prefix + ".weight"].double()
     if lora_type in (None, "none") or (prefix + ".lora_A") not in sd:
         return w
@@ -44,7 +45,7 @@ def merged_linear_weight(sd, prefix, lora_type):
         V = sd[prefix + ".lora_V"].double()
         return w + (B * V) @ (A * U)
     if lora_type == "lora":
-        return w + 2.0 * (B @ A)
+        return w + lora_scale * (B @ A)   # 2 in endodav (alpha = 2r); 1/r in endodac (alpha = 1, endodac.py:222-223)
     if lora_type == "ssb":
         return A.view(1, -1) * w * B
     if lora_type == "dash":
@@ -134,10 +135,10 @@ def pack_state_dict(sd, cfg, dtype=torch.bfloat16):
         vec(n + "proj.b", sd[b + "attn.proj.bias"].double() * g1)
         vec(n + "ln2.w", sd[b + "norm2.weight"])
         vec(n + "ln2.b", sd[b + "norm2.bias"])
-        mat(n + "fc1.w", merged_linear_weight(sd, b + "mlp.fc1", lt))
+        mat(n + "fc1.w", merged_linear_weight(sd, b + "mlp.fc1", lt, cfg.get("lora_scale", 2.0)))
         vec(n + "fc1.b", sd[b + "mlp.fc1.bias"])
         g2 = sd[b + "ls2.gamma"].double()
-        mat(n + "fc2.w", merged_linear_weight(sd, b + "mlp.fc2", lt) * g2[:, None])
+        mat(n + "fc2.w", merged_linear_weight(sd, b + "mlp.fc2", lt, cfg.get("lora_scale", 2.0)) * g2[:, None])
         vec(n + "fc2.b", sd[b + "mlp.fc2.bias"].double() * g2)
         if i in cfg.get("residual_block_indexes", []):
             rb = b + "residual_."
@@ -202,7 +203,7 @@ def pack_state_dict(sd, cfg, dtype=torch.bfloat16):
 
     mm_ch = [oc[2], oc[3], F, F]
     tl = lt if cfg.get("temporal_lora", False) else "none"
-    for j in range(4):
+    for j in range(4 if cfg.get("motion", True) else 0):   # motion=False: the endodac image model
         C = mm_ch[j]
         thd = C // 8
         t = h + "motion_modules.%d.temporal_transformer." % j

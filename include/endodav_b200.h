@@ -61,6 +61,8 @@ typedef struct edv_config {
   int32_t rope;            /* 0: sinusoidal APE rows added by the LayerNorm that feeds q|k|v; 1: RoPE on q,k */
   int32_t dtype;           /* edv_dtype */
   int32_t engine;          /* edv_engine */
+  int32_t no_motion;       /* 1: no temporal modules -- the `endodac` image model (models/endodac/endodac.py:14-127) */
+  int32_t no_normalize;    /* 1: frames enter the patch embedding un-normalised (endodac pre_norm=False, endodac.py:208-211) */
 } edv_config;
 
 /* --- context ---------------------------------------------------------------------------- */

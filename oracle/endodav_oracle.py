@@ -68,10 +68,12 @@ class _Ctx:
         return F.conv2d(self.q(x), self.q(w), b, stride=stride, padding=padding)
 
 
-def merged_lora_weight(sd, prefix, lora_type, r):
+def merged_lora_weight(sd, prefix, lora_type, r, lora_scale=2.0):
     """Effective (out,in) weight of a LoRA-family linear at inference.
 
     Linear     : W + (alpha/r) B A, alpha = 2r            (endodav.py:111; layers.py:148-157)
+                 endodac leaves lora_alpha at its default 1 -> alpha/r = 1/r (endodac.py:222-223);
+                 that is ``lora_scale``
     DVLinear   : W + (alpha/r)(B*V)(A*U), alpha = r       (endodav.py:108; layers.py:384-393)
     Linear_SSB : A.view(1,in) * W * B(out,1)              (layers.py:423-430)
     DashLinear : W + 2 B A + U_top diag(idx) Vt_top       (layers.py:553-582, post-warm-up form)
@@ -84,7 +86,7 @@ def merged_lora_weight(sd, prefix, lora_type, r):
         U, V = sd[prefix + ".lora_U"], sd[prefix + ".lora_V"]
         return w + 1.0 * ((B * V) @ (A * U))
     if lora_type == "lora":
-        return w + 2.0 * (B @ A)
+        return w + lora_scale * (B @ A)
     if lora_type == "ssb":
         return A.view(1, -1) * w * B
     if lora_type == "dash":
@@ -107,7 +109,7 @@ def lora_linear_unmerged(c, x, prefix, lora_type):
     if lora_type == "dvlora":
         U, V = sd[prefix + ".lora_U"], sd[prefix + ".lora_V"]
         return out + (x @ (A * U).T @ (B * V).T) * 1.0
-    out = out + (x @ A.T @ B.T) * 2.0
+    out = out + (x @ A.T @ B.T) * (c.cfg.get("lora_scale", 2.0) if lora_type == "lora" else 2.0)
     if lora_type == "dash":
         ut, vt, idx = sd[prefix + ".weight_u_top"], sd[prefix + ".weight_vt_top"], sd[prefix + ".lora_index"]
         out = out + x @ (ut @ torch.diag(idx) @ vt).T
@@ -183,8 +185,8 @@ def encoder_taps(c, x_norm, unmerged=False):
             y = F.gelu(lora_linear_unmerged(c, y, b + "mlp.fc1", lt))
             y = lora_linear_unmerged(c, y, b + "mlp.fc2", lt)
         else:
-            y = F.gelu(c.linear(y, merged_lora_weight(sd, b + "mlp.fc1", lt, cfg["r"]), sd[b + "mlp.fc1.bias"]))
-            y = c.linear(y, merged_lora_weight(sd, b + "mlp.fc2", lt, cfg["r"]), sd[b + "mlp.fc2.bias"])
+            y = F.gelu(c.linear(y, merged_lora_weight(sd, b + "mlp.fc1", lt, cfg["r"], cfg.get("lora_scale", 2.0)), sd[b + "mlp.fc1.bias"]))
+            y = c.linear(y, merged_lora_weight(sd, b + "mlp.fc2", lt, cfg["r"], cfg.get("lora_scale", 2.0)), sd[b + "mlp.fc2.bias"])
         x = x + y * sd[b + "ls2.gamma"]
         if i in cfg["residual_block_indexes"]:
             # block.py:146-150 -- patch_h/patch_w are fixed at construction (224x280 only)
@@ -193,7 +195,7 @@ def encoder_taps(c, x_norm, unmerged=False):
             x = torch.cat((x[:, :1], x[:, 1:] + r_), dim=1)
         if i in (0,):
             c.rec("block0", x)
-        if i in TAPS[cfg["encoder"]]:
+        if i in (cfg.get("taps") or TAPS[cfg["encoder"]]):
             t = F.layer_norm(x, (D,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
             taps.append(t[:, 1:])
     for i, t in enumerate(taps):
@@ -316,8 +318,10 @@ def dpt_head(c, taps, ph, pw, T, unmerged=False, inv_sigmoid=False, out_sigmoid=
     l1, l2, l3, l4 = outs
     for i, l in enumerate(outs):
         c.rec("layer%d" % (i + 1), l)
-    l3 = temporal_module(c, l3, 0, B, T, unmerged)
-    l4 = temporal_module(c, l4, 1, B, T, unmerged)
+    motion = cfg.get("motion", True)   # False: endodac's DPTHead (models/endodac/endodac.py:93-127)
+    if motion:
+        l3 = temporal_module(c, l3, 0, B, T, unmerged)
+        l4 = temporal_module(c, l4, 1, B, T, unmerged)
     c.rec("mm0", l3)
     c.rec("mm1", l4)
     s = h + "scratch."
@@ -327,9 +331,11 @@ def dpt_head(c, taps, ph, pw, T, unmerged=False, inv_sigmoid=False, out_sigmoid=
     l4r = c.conv(l4, sd[s + "layer4_rn.weight"], padding=1)
     p4 = _fusion(c, s + "refinenet4.", l4r, size=l3r.shape[2:])
     c.rec("path4_pre", p4)
-    p4 = temporal_module(c, p4, 2, B, T, unmerged)
+    if motion:
+        p4 = temporal_module(c, p4, 2, B, T, unmerged)
     p3 = _fusion(c, s + "refinenet3.", p4, l3r, size=l2r.shape[2:])
-    p3 = temporal_module(c, p3, 3, B, T, unmerged)
+    if motion:
+        p3 = temporal_module(c, p3, 3, B, T, unmerged)
     c.rec("path3", p3)
     p2 = _fusion(c, s + "refinenet2.", p3, l2r, size=l1r.shape[2:])
     p1 = _fusion(c, s + "refinenet1.", p2, l1r)
@@ -371,3 +377,42 @@ def forward(sd, x, cfg=None, image_shape=(224, 280), emulate_bf16=False, unmerge
     ph, pw = xn.shape[-2] // 14, xn.shape[-1] // 14
     taps = encoder_taps(c, xn, unmerged)
     return dpt_head(c, taps, ph, pw, T, unmerged, inv_sigmoid, out_sigmoid)
+
+
+@torch.no_grad()
+def forward_endodac(sd, x, cfg, image_shape=(224, 280), pre_norm=False, inv_sigmoid=False, emulate_bf16=False,
+                    unmerged=False, record=None):
+    """endodac.forward (models/endodac/endodac.py:246-259): the image model -- same encoder and DPT
+    head as endodav, no temporal modules, ``depth_head.*`` checkpoint keys, and NO input normalisation
+    unless ``pre_norm`` (:208-211).  x [B,3,H,W] or [B,T,3,H,W] in [0,1]; ``cfg`` from
+    ``weights.endodac_cfg``.  Returns {("disp", s): [B,1,h_s,w_s]}."""
+    from .weights import from_endodac_keys
+
+    cfg = full_cfg(cfg)
+    assert not cfg["motion"]
+    sd = {k: v.float() for k, v in from_endodac_keys(sd).items()}
+    c = _Ctx(sd, cfg, emulate_bf16, record)
+    if x.dim() == 5:
+        x = x.flatten(0, 1)
+    xr = F.interpolate(x.float(), size=tuple(image_shape), mode="bilinear", align_corners=True)
+    if pre_norm:
+        xr = (xr - torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)) / torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    ph, pw = xr.shape[-2] // 14, xr.shape[-1] // 14
+    taps = encoder_taps(c, xr, unmerged)
+    return dpt_head(c, taps, ph, pw, 1, unmerged, inv_sigmoid, False)
+
+
+@torch.no_grad()
+def infer_video_depth_endodac(sd, frames, cfg, image_shape, batch_size=8, **kw):
+    """endodac.infer_video_depth (endodac.py:261-272): independent chunks, bilinear resize back."""
+    import numpy as np
+
+    H, W = frames[0].shape[:2]
+    outs = []
+    for c0 in range(0, len(frames), batch_size):
+        chunk = frames[c0:c0 + batch_size].astype(np.float32) / 255.
+        t = torch.from_numpy(np.transpose(chunk, (0, 3, 1, 2))).float()
+        d = forward_endodac(sd, t, cfg, image_shape, **kw)[("disp", 0)]
+        d = F.interpolate(d, size=(H, W), mode="bilinear", align_corners=True)[:, 0]
+        outs.append(d.numpy())
+    return np.concatenate(outs, axis=0)

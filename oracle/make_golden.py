@@ -51,6 +51,62 @@ VIDEO_CASES = {
 
 STUB_VIDEO_N = [1, 5, 21, 22, 23, 32, 44, 45, 100]
 
+# endodac image model: name -> (reference ctor kwargs, input shape, weight seed, frame seed)
+ENDODAC_CASES = {
+    "dac_small_dvlora": (dict(backbone_size="small", lora_type="dvlora", image_shape=(42, 56), disable_conv_head=True),
+                         (3, 3, 48, 64), 71, 72),
+    "dac_small_prenorm_5d": (dict(backbone_size="small", lora_type="lora", image_shape=(56, 56), disable_conv_head=True,
+                                  pre_norm=True), (2, 2, 3, 56, 56), 73, 74),
+    "dac_base_lora_convhead": (dict(backbone_size="base", lora_type="lora", image_shape=(56, 70), disable_conv_head=False,
+                                    inv_sigmoid=True), (2, 3, 56, 70), 75, 76),
+    "dac_base_dvlora": (dict(backbone_size="base", lora_type="dvlora", image_shape=(70, 56), disable_conv_head=True),
+                        (2, 3, 70, 56), 77, 78),
+}
+ENDODAC_VIDEO = {
+    # name -> (ctor kwargs, N, H, W, batch_size, weight seed, frame seed)
+    "dac_video_n11": (dict(backbone_size="small", lora_type="dvlora", image_shape=(28, 42), disable_conv_head=True),
+                      11, 40, 56, 4, 79, 80),
+}
+
+
+def endodac_oracle_cfg(kw):
+    return weights.endodac_cfg(kw["backbone_size"], kw.get("lora_type", "lora"), kw.get("r", 4),
+                               kw.get("residual_block_indexes", []), kw.get("disable_conv_head", False))
+
+
+def make_endodac(manifest):
+    for name, (kw, shape, wseed, fseed) in ENDODAC_CASES.items():
+        cfg = endodac_oracle_cfg(kw)
+        sd = weights.to_endodac_keys(weights.make_state_dict(cfg, wseed))
+        model = ref_import.build_reference_endodac(dict(kw, r=4))
+        missing = model.load_state_dict(sd, strict=True)
+        n = 1
+        for d in shape[:-3]:
+            n *= d
+        x = weights.make_frames(1, n, shape[-2], shape[-1], fseed)[0].reshape(shape)
+        with torch.no_grad():
+            out = model(x)
+        arrays = {"disp%d" % s: out[("disp", s)].numpy().astype(np.float32) for s in range(4)}
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
+        manifest[name] = dict(kind="endodac_forward", ctor={k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()},
+                              input=list(shape), weight_seed=wseed, frame_seed=fseed, keys=len(sd))
+        print(name, {k: v.shape for k, v in arrays.items()}, float(arrays["disp0"].mean()), str(missing))
+        if name in ("dac_small_dvlora", "dac_base_lora_convhead"):
+            with open(os.path.join(GOLDEN_DIR, "state_dict_keys_%s.json" % name), "w") as f:
+                json.dump([[k, list(v.shape)] for k, v in model.state_dict().items()], f)
+    for name, (kw, N, H, W, bs, wseed, fseed) in ENDODAC_VIDEO.items():
+        cfg = endodac_oracle_cfg(kw)
+        sd = weights.to_endodac_keys(weights.make_state_dict(cfg, wseed))
+        model = ref_import.build_reference_endodac(dict(kw, r=4))
+        model.load_state_dict(sd, strict=True)
+        v = weights.make_video_u8(N, H, W, fseed)
+        with torch.no_grad():
+            out = model.infer_video_depth(v, batch_size=bs, device="cpu")
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), depth=out.astype(np.float32))
+        manifest[name] = dict(kind="endodac_video", ctor={k: (list(v_) if isinstance(v_, tuple) else v_) for k, v_ in kw.items()},
+                              input=[N, H, W], batch_size=bs, weight_seed=wseed, frame_seed=fseed)
+        print(name, out.shape, float(out.mean()))
+
 
 def ctor_kwargs(over, image_shape):
     enc = over.get("encoder", "vits")
@@ -88,6 +144,13 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref_mod = ref_import.import_reference()
     manifest = {}
+    if "--endodac-only" in sys.argv:   # add the endodac fixtures without regenerating the others
+        with open(os.path.join(GOLDEN_DIR, "manifest.json")) as f:
+            manifest = json.load(f)
+        make_endodac(manifest)
+        with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
+            json.dump(manifest, f, indent=1)
+        return
     for name, (over, ishape, (B, T, H, W), wseed, fseed) in FORWARD_CASES.items():
         kw = ctor_kwargs(over, ishape)
         cfg = oracle_cfg(kw)
@@ -143,6 +206,8 @@ def main():
             stub["n%d" % N] = model.infer_video_depth(v, device="cpu").astype(np.float32)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "video_stub.npz"), **stub)
     manifest["video_stub"] = dict(kind="video_stub", n=STUB_VIDEO_N, input=[30, 44], image_shape=[28, 42])
+
+    make_endodac(manifest)
 
     with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)

@@ -82,3 +82,15 @@ def build_reference_model(cfg: dict):
         warnings.simplefilter("ignore")
         m = ref_mod.endodav(**cfg)
     return m.eval()
+
+
+def build_reference_endodac(kw: dict):
+    """Instantiate the reference image model ``endodac`` (models/endodac/endodac.py:144) unmodified."""
+    import importlib
+
+    import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("models.endodac.endodac")
+        m = mod.endodac(**kw)
+    return m.eval()

@@ -22,6 +22,8 @@ ENCODERS = {
     # vit_large forgets img_size=518 -> 16x16+1 table)
     "vits": dict(dim=384, depth=12, heads=6, pos_tokens=37 * 37 + 1),
     "vitl": dict(dim=1024, depth=24, heads=16, pos_tokens=16 * 16 + 1),
+    # endodac "base" backbone (vision_transformer.py:368-382; models/endodac/endodac.py:171-199)
+    "vitb": dict(dim=768, depth=12, heads=12, pos_tokens=37 * 37 + 1),
 }
 
 DEFAULT_CFG = dict(
@@ -35,6 +37,9 @@ DEFAULT_CFG = dict(
     residual_block_indexes=[],
     temporal_lora=False,
     disable_conv_head=True,
+    motion=True,   # False: the endodac image model (same head, no temporal modules)
+    taps=None,     # None: the encoder's table (endodav.py:76-79)
+    lora_scale=2.0,  # lora_type="lora": alpha/r with alpha = 2r (endodav.py:111)
 )
 
 
@@ -173,7 +178,7 @@ def make_state_dict(cfg=None, seed=1234):
         g.weight(s + "output_conv2.2.weight", (1, 32, 1, 1), 0.5)
         g.sd[s + "output_conv2.2.bias"] = torch.full((1,), 1.0)
     mm_ch = [oc[2], oc[3], F, F]
-    for j in range(4):
+    for j in range(4 if cfg["motion"] else 0):
         C = mm_ch[j]
         t = h + "motion_modules.%d.temporal_transformer." % j
         g.norm(t + "norm", C)
@@ -207,6 +212,36 @@ def make_state_dict(cfg=None, seed=1234):
             g.weight(c + "4.weight", (1, 32, 1, 1))
             g.bias(c + "4.bias", 1)
     return g.sd
+
+
+ENDODAC_SIZES = {  # models/endodac/endodac.py:171-199
+    "small": dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384]),
+    "base": dict(encoder="vitb", features=128, out_channels=[96, 192, 384, 768]),
+}
+
+
+def endodac_cfg(backbone_size="small", lora_type="dvlora", r=4, residual_block_indexes=(), disable_conv_head=True):
+    """Oracle cfg of the reference ``endodac`` constructor (models/endodac/endodac.py:153-231)."""
+    c = dict(ENDODAC_SIZES[backbone_size])
+    c.update(lora_type=lora_type if lora_type in ("lora", "dvlora") else "none", r=r,
+             residual_block_indexes=list(residual_block_indexes), disable_conv_head=disable_conv_head,
+             temporal_lora=False, motion=False)
+    # endodac.forward calls get_intermediate_layers(x, 4, ...) (endodac.py:254): an int n means the LAST
+    # n blocks (vision_transformer.py:292-293), not the [2,5,8,11] table the class also defines (:183-186)
+    depth = ENCODERS[c["encoder"]]["depth"]
+    c["taps"] = list(range(depth - 4, depth))
+    # LoraLinear(..., r=r) without lora_alpha -> scaling = 1/r (endodac.py:222-223; mylora/layers.py:99,114)
+    c["lora_scale"] = 1.0 / r
+    return full_cfg(c)
+
+
+def to_endodac_keys(sd):
+    """endodav-layout keys -> the ``endodac`` checkpoint layout (``head.`` is ``depth_head.`` there)."""
+    return OrderedDict((("depth_head." + k[5:]) if k.startswith("head.") else k, v) for k, v in sd.items())
+
+
+def from_endodac_keys(sd):
+    return OrderedDict((("head." + k[11:]) if k.startswith("depth_head.") else k, v) for k, v in sd.items())
 
 
 def make_frames(B, T, H, W, seed=4321):

@@ -57,7 +57,7 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
     xr = F.interpolate(x.flatten(0, 1).float(), size=(h, w), mode="bilinear", align_corners=True)
     mean = torch.tensor((0.485, 0.456, 0.406)).view(1, 3, 1, 1)
     std = torch.tensor((0.229, 0.224, 0.225)).view(1, 3, 1, 1)
-    xn = (xr - mean) / std
+    xn = (xr - mean) / std if cfg.get("normalize", True) else xr   # endodac pre_norm=False: edv_config.no_normalize
     # im2col in (c, ky, kx) order, zero padded to 640
     A0 = F.unfold(xn, kernel_size=14, stride=14).transpose(1, 2).reshape(BT * P, 588)
     A0 = F.pad(A0, (0, pk["patch.w"].shape[1] - 588))
@@ -146,8 +146,9 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
         hs = hs + _lin(gg, pk[n + "ff2.w"], pk[n + "ff2.b"])
         return (_lin(hs, pk[n + "pout.w"], pk[n + "pout.b"]) + X.reshape(Fr * hw, C)).reshape(Fr, hh_, ww_, C)
 
-    L3m = motion(0, L3)
-    L4m = motion(1, L4)
+    mm_on = cfg.get("motion", True)   # endodac: edv_config.no_motion
+    L3m = motion(0, L3) if mm_on else L3
+    L4m = motion(1, L4) if mm_on else L4
     rec("mm0", L3m[..., : oc[2]].permute(0, 3, 1, 2))
     rec("mm1", L4m[..., : oc[3]].permute(0, 3, 1, 2))
     l1r = _conv3(L1, pk["rn1.w"])
@@ -170,9 +171,9 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
 
     p4 = fusion(4, l4r, None, ph, pw)
     rec("path4_pre", p4.permute(0, 3, 1, 2))
-    p4m = motion(2, p4)
+    p4m = motion(2, p4) if mm_on else p4
     p3 = fusion(3, p4m, l3r, 2 * ph, 2 * pw)
-    p3m = motion(3, p3)
+    p3m = motion(3, p3) if mm_on else p3
     rec("path3", p3m.permute(0, 3, 1, 2))
     p2 = fusion(2, p3m, l2r, 4 * ph, 4 * pw)
     p1 = fusion(1, p2, l1r, 8 * ph, 8 * pw)
@@ -192,8 +193,9 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
         for s in (1, 2, 3):
             out[("disp", s)] = F.interpolate(out[("disp", s - 1)], scale_factor=0.5, mode="bilinear", align_corners=True)
     else:
-        out[("disp", 3)] = head("cd4.c0", "cd4.c2", "cd4.c4", p4m, 2 * ph, 2 * pw, 1.0)
-        out[("disp", 2)] = head("cd3.c0", "cd3.c2", "cd3.c4", p3m, 4 * ph, 4 * pw, 1.0)
-        out[("disp", 1)] = head("cd2.c0", "cd2.c2", "cd2.c4", p2, 8 * ph, 8 * pw, 1.0)
-        out[("disp", 0)] = head("cd1.c0", "cd1.c2", "cd1.c4", p1, 16 * ph, 16 * pw, 1.0)
+        sg = -1.0 if cfg.get("inv_sigmoid", False) else 1.0
+        out[("disp", 3)] = head("cd4.c0", "cd4.c2", "cd4.c4", p4m, 2 * ph, 2 * pw, sg)
+        out[("disp", 2)] = head("cd3.c0", "cd3.c2", "cd3.c4", p3m, 4 * ph, 4 * pw, sg)
+        out[("disp", 1)] = head("cd2.c0", "cd2.c2", "cd2.c4", p2, 8 * ph, 8 * pw, sg)
+        out[("disp", 0)] = head("cd1.c0", "cd1.c2", "cd1.c4", p1, 16 * ph, 16 * pw, sg)
     return out
