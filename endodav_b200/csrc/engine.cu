@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ops.cuh"
+#include "stitch.cuh"
 
 using namespace edv;
 
@@ -935,6 +936,42 @@ int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int
   Launch L;
   L.stream = (cudaStream_t)stream;
   resize_f32(L, X, Y, F, h, w, oh, ow);
+  return finish(L);
+}
+
+int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_dev, double* scratch_dev,
+                         float* scale_shift_dev, void* stream) {
+  if (!win_dev || !out_dev || !scratch_dev || !scale_shift_dev || k < 0 || H < 1 || W < 1) return EDV_ERR_ARG;
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  const long long hw = (long long)H * W;
+  if (k == 0) {
+    // depth_list_aligned += depth_list[:INFER_LEN] (endodav.py:220-221)
+    cudaError_t e = cudaMemcpyAsync(out_dev, win_dev, (size_t)32 * hw * sizeof(float), cudaMemcpyDeviceToDevice, L.stream);
+    if (e != cudaSuccess) return EDV_ERR_CUDA;
+    stitch_identity_kernel<<<1, 1, 0, L.stream>>>(scale_shift_dev);
+    L.check("stitch_identity");
+    return finish(L);
+  }
+  const long long pos = 32 + 22LL * (k - 1);        // frames aligned so far
+  float* tail = out_dev + (pos - 8) * hw;            // depth_list_aligned[-INTERP_LEN:]
+  const long long n = 8 * hw;
+  float* ss = scale_shift_dev + 2 * (long long)k;
+  L.note(0, (double)n * 8);
+  stitch_stats_kernel<<<STITCH_BLOCKS, STITCH_THREADS, 0, L.stream>>>(tail, win_dev + 2 * hw, n, scratch_dev);
+  L.check("stitch_stats");
+  stitch_solve_kernel<<<1, 32, 0, L.stream>>>(scratch_dev, STITCH_BLOCKS, n, ss);
+  L.check("stitch_solve");
+  StitchFade f;
+  const double step = (1.0 - 0.0) / 7;               // get_interpolate_frames (utils/util.py:65-74)
+  for (int i = 0; i < 8; ++i) {
+    const double w = i == 0 ? 0.0 : (i == 7 ? 1.0 : i * step);
+    f.w1[i] = (float)w;
+    f.w0[i] = (float)(1 - w);
+  }
+  L.note(0, (double)hw * (30 + 30 + 8) * 4);
+  stitch_apply_kernel<<<nblk(30 * hw, 256), 256, 0, L.stream>>>(win_dev, tail, hw, ss, f);
+  L.check("stitch_apply");
   return finish(L);
 }
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_op_linear", "edv_op_conv3x3",
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
     "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
-    "edv_op_disp_head", "edv_op_cubic_resize_u8",
+    "edv_op_disp_head", "edv_op_cubic_resize_u8", "edv_op_stitch_window",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library():
     lib.edv_op_temporal_attention.argtypes = [ci, vp, vp, ci, ci, ci, ci, vp]
     lib.edv_op_disp_head.argtypes = [ci, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, vp]
     lib.edv_op_cubic_resize_u8.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.edv_op_stitch_window.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
     lib.edv_op_layernorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ctypes.c_float, vp]
     lib.edv_op_groupnorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
     lib.edv_op_upsample.argtypes = [ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
@@ -305,3 +306,15 @@ def op_resize_f32(X, oh, ow):
     Y = torch.empty(F, oh, ow, dtype=torch.float32, device=X.device)
     _check(lib.edv_op_resize_f32(_ptr(X), _ptr(Y), F, h, w, oh, ow, _stream()), None, "edv_op_resize_f32")
     return Y
+
+
+STITCH_SCRATCH_DOUBLES = 296 * 4
+
+
+def op_stitch_window(win, k, out, scratch, scale_shift):
+    """Append window k ([32,H,W] float32, device) to the stitched sequence ``out`` ([32+22*(nwin-1),H,W]) on the
+    current stream: the reference's scale/shift alignment + cross-fade (endodav.py:213-254), no host sync."""
+    lib = load_library()
+    _, H, W = win.shape
+    _check(lib.edv_op_stitch_window(_ptr(win), int(k), H, W, _ptr(out), _ptr(scratch), _ptr(scale_shift), _stream()), None,
+           "edv_op_stitch_window")

@@ -14,6 +14,8 @@ are independent.  Rank r of W runs windows k = r, r+W, ... and one NCCL gather m
 per-window disparity to rank 0 (``torch.distributed``); there is no collective inside the
 network.  With torch.distributed not initialised this is the single-GPU path.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -135,6 +137,63 @@ class _FrameCache:
         return t
 
 
+def final_frame_range(k, n_windows, n_frames):
+    """Output frames that become final once window k is stitched: everything but the 8-frame tail the next
+    window will cross-fade (the last window finalises its tail too), clipped to the video length."""
+    lo = 0 if k == 0 else INFER_LEN + STEP * (k - 1) - INTERP_LEN
+    hi = INFER_LEN + STEP * (n_windows - 1) if k == n_windows - 1 else INFER_LEN + STEP * k - INTERP_LEN
+    return min(lo, n_frames), min(hi, n_frames)
+
+
+class _GpuStitcher:
+    """Device-side replacement of ``stitch_windows`` (endodav.py:213-254): windows are pushed in order, each
+    one is aligned and cross-faded by ``edv_op_stitch_window`` on the current stream; ``finish`` returns the
+    float32 [n_frames,H,W] host array."""
+
+    RING = 4
+
+    def __init__(self, n_windows, n_frames, H, W, device, ring=True):
+        from . import engine as _engine
+
+        self._op = _engine.op_stitch_window
+        self.nwin, self.n, self.k = n_windows, n_frames, 0
+        self.seq = torch.empty(INFER_LEN + STEP * (n_windows - 1), H, W, dtype=torch.float32, device=device)
+        self.scratch = torch.empty(_engine.STITCH_SCRATCH_DOUBLES, dtype=torch.float64, device=device)
+        self.scale_shift = torch.empty(n_windows, 2, dtype=torch.float32, device=device)
+        self.out = np.empty((n_frames, H, W), dtype=np.float32) if ring else None
+        self.slots = [torch.empty(INFER_LEN, H, W, dtype=torch.float32).pin_memory() for _ in range(self.RING)] if ring else None
+        self.pending = []
+
+    def _drain(self, keep):
+        while len(self.pending) > keep:
+            lo, hi, slot, ev = self.pending.pop(0)
+            ev.synchronize()
+            self.out[lo:hi] = slot[: hi - lo].numpy()
+
+    def push(self, win):
+        """win: [32,H,W] float32 device tensor = window ``self.k`` resized to the frame size."""
+        k = self.k
+        self._op(win, k, self.seq, self.scratch, self.scale_shift)
+        self.k += 1
+        if self.slots is None:
+            return
+        lo, hi = final_frame_range(k, self.nwin, self.n)
+        if hi > lo:
+            self._drain(self.RING - 1)
+            slot = self.slots[k % self.RING]
+            slot[: hi - lo].copy_(self.seq[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.pending.append((lo, hi, slot, ev))
+
+    def finish(self):
+        assert self.k == self.nwin
+        if self.slots is None:
+            return self.seq[: self.n].cpu().numpy()
+        self._drain(0)
+        return self.out
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -169,8 +228,6 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         if next(model.parameters()).device != dev:
             model.to(dev)
         eng = model._ensure_engine(ih // 14, iw // 14)
-        import os
-
         from . import engine as _engine
 
         gpu_pre = os.environ.get("ENDODAV_PREPROCESS", "gpu").lower() != "host"
@@ -205,8 +262,19 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                 x = _engine.op_cubic_resize_u8(xu8, new_h, new_w).view(1, INFER_LEN, 3, new_h, new_w)
             return eng.forward(x, resize_to=(H, W), want_pyramid=False)[1]
 
+        gpu_stitch = os.environ.get("ENDODAV_STITCH", "gpu").lower() != "host"
+        if world == 1 and gpu_stitch:
+            # Single GPU, default: every window is aligned / cross-faded on the device right behind its forward
+            # (edv_op_stitch_window, no host sync); the frames a window makes final are copied back through a
+            # small pinned ring while the next windows run.
+            with torch.cuda.device(dev):
+                eng.plan(1, INFER_LEN, new_h, new_w, ih, iw)
+                st = _GpuStitcher(nwin, n, H, W, dev)
+                for j in range(nwin):
+                    st.push(launch(j))
+                return st.finish()
         if world == 1:
-            # Single GPU: stream the windows.  Window j+2 is enqueued before window j is handed to the
+            # ENDODAV_STITCH=host -- the reference's numpy chain: stream the windows.  Window j+2 is enqueued before window j is handed to the
             # (strictly sequential, host-side) stitching, and every result comes back through a small
             # ring of pinned buffers, so GPU work, D2H copies and the numpy stitching overlap.
             AHEAD, RING = 2, 3
@@ -258,6 +326,12 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
     dist.gather(pad, gathered, dst=0)
     if rank != 0:
         return None
+    if forward_window is None and gpu_stitch:
+        with torch.cuda.device(local_t.device):
+            st = _GpuStitcher(nwin, n, H, W, local_t.device, ring=False)
+            for k in range(nwin):
+                st.push(gathered[k % world][k // world])
+            return st.finish()
     host = [g.cpu().numpy() for g in gathered]
     wins = [host[k % world][k // world] for k in range(nwin)]
     return stitch_windows(wins, n)

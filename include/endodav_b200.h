@@ -173,6 +173,17 @@ int edv_op_upsample(int dtype, const void* X, void* Y, int F, int h, int w, int 
  * (dpt_pyramid.py:95-97) and the final resize of infer_video_depth (endodav.py:205). */
 int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int ow, void* stream);
 
+/* On-GPU stitching of infer_video_depth, one window per call (stream-ordered, no host sync):
+ * window k [32,H,W] float32 (already resized to the frame size) is aligned to the frames stitched so
+ * far by the reference's least-squares (scale, shift) over the 8 overlap frames, clamped at 0, its
+ * overlap cross-faded into out_dev's last 8 frames and its 22 fresh frames appended; k = 0 copies the
+ * 32 frames.  out_dev holds 32 + 22*(n_windows-1) frames; scratch_dev >= 296*4 doubles;
+ * scale_shift_dev [n_windows][2] receives (scale, shift) of every window.  Windows must be submitted in
+ * order k = 0,1,2,...  Replaces endodav.py:213-254 + utils/util.py:40-74 (compute_scale_and_shift_full,
+ * get_interpolate_frames) -- float32 arithmetic op for op, the five sums accumulated in float64. */
+int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_dev, double* scratch_dev,
+                         float* scale_shift_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

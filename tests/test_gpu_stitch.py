@@ -1,0 +1,97 @@
+"""On-GPU window stitching (edv_op_stitch_window) against the reference's numpy chain
+(video.stitch_windows == endodav.py:213-254, itself pinned bit-exactly by tests/golden/video_stub.npz)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from endodav_b200 import engine as eng  # noqa: E402
+from endodav_b200 import video as V  # noqa: E402
+from oracle import weights  # noqa: E402
+from golden_util import load_case  # noqa: E402
+
+
+def _windows(nwin, H, W, seed, spread=0.3):
+    rng = np.random.default_rng(seed)
+    base = rng.random((H, W), dtype=np.float32) * spread + 0.5
+    wins = []
+    for k in range(nwin):
+        a, b = 0.7 + 0.6 * rng.random(), 0.2 * rng.random() - 0.1
+        w = (base[None] * (1 + 0.3 * np.sin(np.arange(32, dtype=np.float32) * 0.3 + k))[:, None, None]
+             + 0.05 * rng.standard_normal((32, H, W)).astype(np.float32))
+        wins.append((a * w + b).astype(np.float32))
+    return wins
+
+
+def _gpu_stitch(wins, n, ring):
+    H, W = wins[0].shape[1:]
+    st = V._GpuStitcher(len(wins), n, H, W, torch.device("cuda"), ring=ring)
+    for w in wins:
+        st.push(torch.from_numpy(w).cuda())
+    out = st.finish()
+    return out, st.scale_shift.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,H,W", [(32, 8, 12), (33, 7, 9), (54, 30, 44), (100, 64, 80), (230, 256, 320)])
+@pytest.mark.parametrize("ring", [True, False])
+def test_stitch_matches_numpy_chain(n, H, W, ring):
+    nwin = V.num_windows(n)
+    wins = _windows(nwin, H, W, n)
+    ref = V.stitch_windows(wins, n)
+    got, ss = _gpu_stitch(wins, n, ring)
+    assert got.shape == ref.shape and got.dtype == np.float32
+    # window 0 is copied: bit-exact; later frames differ only through the (scale, shift) solve, whose five
+    # float32 sums are accumulated in float64 here and pairwise in float32 by numpy
+    assert np.array_equal(got[:min(n, 24)], ref[:min(n, 24)])
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, float(np.abs(ref).max())), float(np.abs(got - ref).max())
+    assert ss[0, 0] == 1.0 and ss[0, 1] == 0.0
+
+
+def test_stitch_given_same_scale_shift_is_bit_exact():
+    """Feeding windows that are already aligned (scale 1, shift 0 solves exactly when post == pre) the apply
+    step must reproduce numpy bit for bit: float32 multiply / add without FMA contraction, clamp, cross-fade."""
+    H, W, nwin = 16, 20, 4
+    rng = np.random.default_rng(3)
+    wins = [rng.random((32, H, W), dtype=np.float32) for _ in range(nwin)]
+    ref_scales = []
+    # make every solve degenerate (det == 0 -> scale 1, shift 0): constant overlap frames
+    for w in wins:
+        w[2:10] = 0.5
+    wins[0][24:32] = 0.5
+    for k in range(1, nwin):
+        wins[k][24:32] = 0.5
+    ref = V.stitch_windows(wins, 32 + 22 * (nwin - 1))
+    got, ss = _gpu_stitch(wins, 32 + 22 * (nwin - 1), True)
+    assert np.array_equal(ss, np.tile(np.array([[1.0, 0.0]], np.float32), (nwin, 1)))
+    assert np.array_equal(got, ref)
+
+
+def test_negative_values_are_clamped():
+    H, W = 8, 8
+    wins = _windows(3, H, W, 5)
+    wins[1][12:20] -= 5.0                      # fresh frames far below zero after alignment
+    ref = V.stitch_windows(wins, 76)
+    got, _ = _gpu_stitch(wins, 76, True)
+    assert (got >= 0).all() and (ref[40:48] == 0).any()
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_infer_video_depth_gpu_stitch_equals_host_stitch(monkeypatch):
+    import endodav_b200 as E
+    from golden_util import oracle_cfg
+
+    m, arrays = load_case("video_n45")
+    kw = dict(m["ctor"])
+    kw["image_shape"] = tuple(kw["image_shape"])
+    model = E.endodav(dtype="fp32", **kw)
+    model.load_state_dict(weights.make_state_dict(oracle_cfg(m["ctor"]), m["weight_seed"]), strict=True)
+    model = model.cuda().eval()
+    N, H, W = m["input"]
+    v = weights.make_video_u8(N, H, W, m["frame_seed"])
+    a = model.infer_video_depth(v)
+    monkeypatch.setenv("ENDODAV_STITCH", "host")
+    b = model.infer_video_depth(v)
+    assert a.shape == b.shape == arrays["depth"].shape
+    assert np.array_equal(a[:24], b[:24])
+    assert float(np.abs(a - b).max()) <= 2e-5 * max(1.0, float(np.abs(b).max()))

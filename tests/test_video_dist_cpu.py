@@ -89,3 +89,20 @@ def test_window_indices_match_oracle():
         assert len(slots) == video.num_windows(n)
         for k, row in enumerate(slots):
             assert list(video.window_frame_indices(k, n)) == list(row)
+
+
+def test_final_frame_ranges_tile_the_video():
+    """GPU stitcher bookkeeping (video._GpuStitcher): the frames each window finalises are disjoint, in order,
+    cover [0, n) exactly, and never include the 8-frame tail the next window still cross-fades."""
+    from endodav_b200 import video as V
+
+    for n in (1, 5, 21, 22, 23, 32, 33, 44, 45, 54, 100, 2000):
+        nwin = V.num_windows(n)
+        pos = 0
+        for k in range(nwin):
+            lo, hi = V.final_frame_range(k, nwin, n)
+            assert lo == min(pos, n) and hi >= lo
+            if k < nwin - 1:
+                assert hi <= max(V.INFER_LEN + V.STEP * k - V.INTERP_LEN, 0)
+            pos = max(pos, hi)
+        assert pos == n
