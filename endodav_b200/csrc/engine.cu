@@ -939,9 +939,18 @@ int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int
   return finish(L);
 }
 
-int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_dev, double* scratch_dev,
-                         float* scale_shift_dev, void* stream) {
-  if (!win_dev || !out_dev || !scratch_dev || !scale_shift_dev || k < 0 || H < 1 || W < 1) return EDV_ERR_ARG;
+long long edv_op_stitch_plan(int H, int W, int32_t* plan_host, long long cap) {
+  if (H < 1 || W < 1 || 8LL * H * W >= (1LL << 24)) return EDV_ERR_ARG;   // np.sum(ones) must stay exact in float32
+  const std::vector<int> plan = stitch_plan_build(8LL * H * W);
+  if (plan_host && cap >= (long long)plan.size()) memcpy(plan_host, plan.data(), plan.size() * sizeof(int));
+  return (long long)plan.size();
+}
+
+int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_dev, const int32_t* plan_dev, int n_leaves,
+                         float* scratch_dev, float* scale_shift_dev, void* stream) {
+  if (!win_dev || !out_dev || !plan_dev || !scratch_dev || !scale_shift_dev || k < 0 || H < 1 || W < 1 || n_leaves < 1)
+    return EDV_ERR_ARG;
+  if (((uintptr_t)scratch_dev & 15) != 0) return EDV_ERR_ARG;
   Launch L;
   L.stream = (cudaStream_t)stream;
   const long long hw = (long long)H * W;
@@ -957,11 +966,12 @@ int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_d
   float* tail = out_dev + (pos - 8) * hw;            // depth_list_aligned[-INTERP_LEN:]
   const long long n = 8 * hw;
   float* ss = scale_shift_dev + 2 * (long long)k;
+  float4* val = (float4*)scratch_dev;
   L.note(0, (double)n * 8);
-  stitch_stats_kernel<<<STITCH_BLOCKS, STITCH_THREADS, 0, L.stream>>>(tail, win_dev + 2 * hw, n, scratch_dev);
-  L.check("stitch_stats");
-  stitch_solve_kernel<<<1, 32, 0, L.stream>>>(scratch_dev, STITCH_BLOCKS, n, ss);
-  L.check("stitch_solve");
+  stitch_leaf_kernel<<<nblk((long long)n_leaves * 8, STITCH_THREADS), STITCH_THREADS, 0, L.stream>>>(tail, win_dev + 2 * hw, plan_dev, val);
+  L.check("stitch_leaf");
+  stitch_tree_solve_kernel<<<1, 1024, 0, L.stream>>>(plan_dev, val, n, ss);
+  L.check("stitch_tree_solve");
   StitchFade f;
   const double step = (1.0 - 0.0) / 7;               // get_interpolate_frames (utils/util.py:65-74)
   for (int i = 0; i < 8; ++i) {

@@ -21,7 +21,7 @@ EXPORTS = [
     "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_op_linear", "edv_op_conv3x3",
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
     "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
-    "edv_op_disp_head", "edv_op_cubic_resize_u8", "edv_op_stitch_window",
+    "edv_op_disp_head", "edv_op_cubic_resize_u8", "edv_op_stitch_window", "edv_op_stitch_plan",
 ]
 
 
@@ -79,7 +79,8 @@ def load_library():
     lib.edv_op_temporal_attention.argtypes = [ci, vp, vp, ci, ci, ci, ci, vp]
     lib.edv_op_disp_head.argtypes = [ci, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, vp]
     lib.edv_op_cubic_resize_u8.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
-    lib.edv_op_stitch_window.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
+    lib.edv_op_stitch_window.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, vp, vp]
+    lib.edv_op_stitch_plan.argtypes = [ci, ci, vp, ctypes.c_longlong]
     lib.edv_op_layernorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ctypes.c_float, vp]
     lib.edv_op_groupnorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
     lib.edv_op_upsample.argtypes = [ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
@@ -88,6 +89,7 @@ def load_library():
         fn = getattr(lib, name)
         if name not in ("edv_destroy", "edv_last_error"):
             fn.restype = ci
+    lib.edv_op_stitch_plan.restype = ctypes.c_longlong
     _lib = lib
     return lib
 
@@ -169,7 +171,7 @@ class Engine:
             out.append((h.value, w.value))
         return out
 
-    def forward(self, frames, resize_to=None, want_pyramid=True):
+    def forward(self, frames, resize_to=None, want_pyramid=True, resized_out=None):
         """frames: float32 [B,T,3,H,W] (or uint8 [B*T,H,W,3] at network resolution) on this
         device.  Returns (list of 4 disparity tensors [BT,1,h_s,w_s] or None, resized or None)."""
         BT = self.shape_key[0] * self.shape_key[1]
@@ -180,7 +182,9 @@ class Engine:
         oh = ow = 0
         if resize_to is not None:
             oh, ow = resize_to
-            resized = torch.empty(BT, oh, ow, dtype=torch.float32, device=self.device)
+            resized = resized_out if resized_out is not None else torch.empty(BT, oh, ow, dtype=torch.float32, device=self.device)
+            if tuple(resized.shape) != (BT, oh, ow) or resized.dtype != torch.float32 or not resized.is_contiguous():
+                raise EndoDAVError("resized_out must be a contiguous float32 [%d,%d,%d] tensor" % (BT, oh, ow))
         fn = self.lib.edv_forward_u8 if frames.dtype == torch.uint8 else self.lib.edv_forward
         rc = fn(self.ctx, _ptr(frames), arr, _ptr(resized), oh, ow, ctypes.c_void_p(self._ws_ptr()), _stream())
         _check(rc, self.ctx, "edv_forward")
@@ -308,13 +312,25 @@ def op_resize_f32(X, oh, ow):
     return Y
 
 
-STITCH_SCRATCH_DOUBLES = 296 * 4
+def stitch_plan(H, W):
+    """numpy's pairwise-summation tree for the 8*H*W overlap elements as an int32 table (host only, no GPU
+    needed): [L, I, levels, root, level starts..., L+1 leaf offsets, I (left,right) pairs]."""
+    import numpy as np
+
+    lib = load_library()
+    need = lib.edv_op_stitch_plan(H, W, None, 0)
+    if need < 0:
+        raise EndoDAVError("edv_op_stitch_plan(%d,%d) failed (%d): overlap of 8*H*W elements must stay below 2^24" % (H, W, need))
+    plan = np.empty(need, dtype=np.int32)
+    got = lib.edv_op_stitch_plan(H, W, plan.ctypes.data_as(ctypes.c_void_p), need)
+    assert got == need
+    return plan
 
 
-def op_stitch_window(win, k, out, scratch, scale_shift):
+def op_stitch_window(win, k, out, plan_dev, n_leaves, scratch, scale_shift):
     """Append window k ([32,H,W] float32, device) to the stitched sequence ``out`` ([32+22*(nwin-1),H,W]) on the
     current stream: the reference's scale/shift alignment + cross-fade (endodav.py:213-254), no host sync."""
     lib = load_library()
     _, H, W = win.shape
-    _check(lib.edv_op_stitch_window(_ptr(win), int(k), H, W, _ptr(out), _ptr(scratch), _ptr(scale_shift), _stream()), None,
-           "edv_op_stitch_window")
+    _check(lib.edv_op_stitch_window(_ptr(win), int(k), H, W, _ptr(out), _ptr(plan_dev), int(n_leaves), _ptr(scratch),
+                                    _ptr(scale_shift), _stream()), None, "edv_op_stitch_window")

@@ -147,51 +147,36 @@ def final_frame_range(k, n_windows, n_frames):
 
 class _GpuStitcher:
     """Device-side replacement of ``stitch_windows`` (endodav.py:213-254): windows are pushed in order, each
-    one is aligned and cross-faded by ``edv_op_stitch_window`` on the current stream; ``finish`` returns the
-    float32 [n_frames,H,W] host array."""
+    one is aligned and cross-faded by ``edv_op_stitch_window`` on the current stream (no host sync), and the
+    frames it makes final are copied asynchronously into the pinned host array that ``finish`` returns
+    (float32 [n_frames,H,W]; torch's pinned-memory cache recycles it once the caller drops it)."""
 
-    RING = 4
-
-    def __init__(self, n_windows, n_frames, H, W, device, ring=True):
+    def __init__(self, n_windows, n_frames, H, W, device):
         from . import engine as _engine
 
         self._op = _engine.op_stitch_window
         self.nwin, self.n, self.k = n_windows, n_frames, 0
         self.seq = torch.empty(INFER_LEN + STEP * (n_windows - 1), H, W, dtype=torch.float32, device=device)
-        self.scratch = torch.empty(_engine.STITCH_SCRATCH_DOUBLES, dtype=torch.float64, device=device)
+        plan = _engine.stitch_plan(H, W)       # numpy's pairwise-sum tree for the 8*H*W overlap elements
+        self.n_leaves = int(plan[0])
+        self.plan = torch.from_numpy(plan).to(device)
+        self.scratch = torch.empty(4 * int(plan[0] + plan[1]), dtype=torch.float32, device=device)
         self.scale_shift = torch.empty(n_windows, 2, dtype=torch.float32, device=device)
-        self.out = np.empty((n_frames, H, W), dtype=np.float32) if ring else None
-        self.slots = [torch.empty(INFER_LEN, H, W, dtype=torch.float32).pin_memory() for _ in range(self.RING)] if ring else None
-        self.pending = []
-
-    def _drain(self, keep):
-        while len(self.pending) > keep:
-            lo, hi, slot, ev = self.pending.pop(0)
-            ev.synchronize()
-            self.out[lo:hi] = slot[: hi - lo].numpy()
+        self.out = torch.empty(n_frames, H, W, dtype=torch.float32, pin_memory=True)
 
     def push(self, win):
         """win: [32,H,W] float32 device tensor = window ``self.k`` resized to the frame size."""
         k = self.k
-        self._op(win, k, self.seq, self.scratch, self.scale_shift)
+        self._op(win, k, self.seq, self.plan, self.n_leaves, self.scratch, self.scale_shift)
         self.k += 1
-        if self.slots is None:
-            return
         lo, hi = final_frame_range(k, self.nwin, self.n)
         if hi > lo:
-            self._drain(self.RING - 1)
-            slot = self.slots[k % self.RING]
-            slot[: hi - lo].copy_(self.seq[lo:hi], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            self.pending.append((lo, hi, slot, ev))
+            self.out[lo:hi].copy_(self.seq[lo:hi], non_blocking=True)
 
     def finish(self):
         assert self.k == self.nwin
-        if self.slots is None:
-            return self.seq[: self.n].cpu().numpy()
-        self._drain(0)
-        return self.out
+        torch.cuda.current_stream().synchronize()
+        return self.out.numpy()
 
 
 def _dist():
@@ -235,43 +220,56 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         # gpu_pre (default): the raw uint8 frames of the window are uploaded (4x fewer bytes than the
         # resized float clip) and the reference's /255 + cv2 INTER_CUBIC resize + HWC->CHW runs in a
         # CUDA kernel (edv_op_cubic_resize_u8); ENDODAV_PREPROCESS=host keeps the reference's host path.
+        # Windows are independent, so WB of them go through the network as one [WB,32,...] clip batch (the
+        # engine's batched result is bit-identical to the clips run one by one, test_clip_batch_sweep_*):
+        # at 224x280 eight windows take 16.4 ms instead of 8 x 3.7 ms.
+        gpu_stitch = os.environ.get("ENDODAV_STITCH", "gpu").lower() != "host"
+        # default: 8 windows at 224x280, fewer at larger network resolutions (workspace grows with WB*32 frames)
+        wb_default = max(1, min(8, int(round(8.0 * 224 * 280 / (new_h * new_w)))))
+        WB = max(1, int(os.environ.get("ENDODAV_WINDOW_BATCH", wb_default))) if (gpu_stitch or world > 1) else 1
         if gpu_pre:
-            pinned = [torch.empty(INFER_LEN, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            pinned = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
         else:
-            pinned = [torch.empty(1, INFER_LEN, 3, new_h, new_w, dtype=torch.float32).pin_memory() for _ in range(2)]
+            pinned = [torch.empty(WB, INFER_LEN, 3, new_h, new_w, dtype=torch.float32).pin_memory() for _ in range(2)]
         copied = [None, None]
+        calls = [0]
 
-        def launch(j):
-            """enqueue window mine[j]: H2D of its frames, (cubic resize,) forward, resize back -> device tensor"""
-            slot = j & 1
+        def launch(j, nb=1, out=None):
+            """enqueue windows mine[j:j+nb]: H2D of their frames, (cubic resize,) forward, resize back ->
+            device tensor [nb*32,H,W]"""
+            slot = calls[0] & 1
+            calls[0] += 1
             if copied[slot] is not None:
                 copied[slot].synchronize()  # the earlier H2D copy out of this buffer has finished
             buf = pinned[slot]
-            idx = window_frame_indices(mine[j], n)
+            idx = np.concatenate([window_frame_indices(mine[j + b], n) for b in range(nb)])
             if gpu_pre:
-                np.take(frames, idx, axis=0, out=buf.numpy())
-                xu8 = buf.to(dev, non_blocking=True)
+                np.take(frames, idx, axis=0, out=buf.numpy()[: nb * INFER_LEN])
+                xu8 = buf[: nb * INFER_LEN].to(dev, non_blocking=True)
             else:
+                flat = buf.view(WB * INFER_LEN, 3, new_h, new_w)
                 for i, src in enumerate(idx):
-                    buf[0, i].copy_(torch.from_numpy(cache.get(int(src))))
-                x = buf.to(dev, non_blocking=True)
+                    flat[i].copy_(torch.from_numpy(cache.get(int(src))))
+                x = buf[:nb].to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             copied[slot] = ev
             if gpu_pre:
-                x = _engine.op_cubic_resize_u8(xu8, new_h, new_w).view(1, INFER_LEN, 3, new_h, new_w)
-            return eng.forward(x, resize_to=(H, W), want_pyramid=False)[1]
+                x = _engine.op_cubic_resize_u8(xu8, new_h, new_w).view(nb, INFER_LEN, 3, new_h, new_w)
+            eng.plan(nb, INFER_LEN, new_h, new_w, ih, iw)
+            return eng.forward(x, resize_to=(H, W), want_pyramid=False, resized_out=out)[1]
 
-        gpu_stitch = os.environ.get("ENDODAV_STITCH", "gpu").lower() != "host"
         if world == 1 and gpu_stitch:
             # Single GPU, default: every window is aligned / cross-faded on the device right behind its forward
             # (edv_op_stitch_window, no host sync); the frames a window makes final are copied back through a
             # small pinned ring while the next windows run.
             with torch.cuda.device(dev):
-                eng.plan(1, INFER_LEN, new_h, new_w, ih, iw)
                 st = _GpuStitcher(nwin, n, H, W, dev)
-                for j in range(nwin):
-                    st.push(launch(j))
+                for j in range(0, nwin, WB):
+                    nb = min(WB, nwin - j)
+                    d = launch(j, nb).view(nb, INFER_LEN, H, W)
+                    for b in range(nb):
+                        st.push(d[b])
                 return st.finish()
         if world == 1:
             # ENDODAV_STITCH=host -- the reference's numpy chain: stream the windows.  Window j+2 is enqueued before window j is handed to the
@@ -283,8 +281,6 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
 
             def stream():
                 with torch.cuda.device(dev):
-                    eng.plan(1, INFER_LEN, new_h, new_w, ih, iw)
-
                     def enqueue(j):
                         ring[j % RING].copy_(launch(j), non_blocking=True)
                         done[j % RING] = torch.cuda.Event()
@@ -301,12 +297,15 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
 
             return stitch_windows(stream(), n)
 
-        local = []
+        # every window's disparity is written straight into this rank's (padded) slice of the gather
+        per = (nwin + world - 1) // world
         with torch.cuda.device(dev):
-            eng.plan(1, INFER_LEN, new_h, new_w, ih, iw)
-            for j in range(len(mine)):
-                local.append(launch(j))
-        local_t = torch.stack(local, 0) if local else torch.empty(0, INFER_LEN, H, W, dtype=torch.float32, device=dev)
+            local_t = torch.empty(per, INFER_LEN, H, W, dtype=torch.float32, device=dev)
+            for j in range(0, len(mine), WB):
+                nb = min(WB, len(mine) - j)
+                launch(j, nb, local_t[j:j + nb].view(nb * INFER_LEN, H, W))
+            if len(mine) < per:
+                local_t[len(mine):].zero_()
     else:
         local = []
         for k in mine:
@@ -320,15 +319,18 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
 
     # one gather of per-window disparity to rank 0 (padded to the largest shard)
     per = (nwin + world - 1) // world
-    pad = torch.zeros(per, INFER_LEN, H, W, dtype=torch.float32, device=local_t.device)
-    pad[: local_t.shape[0]] = local_t
+    if local_t.shape[0] == per:
+        pad = local_t
+    else:
+        pad = torch.zeros(per, INFER_LEN, H, W, dtype=torch.float32, device=local_t.device)
+        pad[: local_t.shape[0]] = local_t
     gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
     dist.gather(pad, gathered, dst=0)
     if rank != 0:
         return None
     if forward_window is None and gpu_stitch:
         with torch.cuda.device(local_t.device):
-            st = _GpuStitcher(nwin, n, H, W, local_t.device, ring=False)
+            st = _GpuStitcher(nwin, n, H, W, local_t.device)
             for k in range(nwin):
                 st.push(gathered[k % world][k // world])
             return st.finish()

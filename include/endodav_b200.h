@@ -177,12 +177,18 @@ int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int
  * window k [32,H,W] float32 (already resized to the frame size) is aligned to the frames stitched so
  * far by the reference's least-squares (scale, shift) over the 8 overlap frames, clamped at 0, its
  * overlap cross-faded into out_dev's last 8 frames and its 22 fresh frames appended; k = 0 copies the
- * 32 frames.  out_dev holds 32 + 22*(n_windows-1) frames; scratch_dev >= 296*4 doubles;
- * scale_shift_dev [n_windows][2] receives (scale, shift) of every window.  Windows must be submitted in
- * order k = 0,1,2,...  Replaces endodav.py:213-254 + utils/util.py:40-74 (compute_scale_and_shift_full,
- * get_interpolate_frames) -- float32 arithmetic op for op, the five sums accumulated in float64. */
-int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_dev, double* scratch_dev,
-                         float* scale_shift_dev, void* stream);
+ * 32 frames.  Windows must be submitted in order k = 0,1,2,...  out_dev holds 32 + 22*(n_windows-1)
+ * frames; scale_shift_dev [n_windows][2] receives (scale, shift) of every window.
+ * Replaces endodav.py:213-254 + utils/util.py:40-74 (compute_scale_and_shift_full,
+ * get_interpolate_frames) BIT-EXACTLY: float32 arithmetic op for op without FMA contraction, and the
+ * np.sum reductions in numpy's own pairwise association order.  That order is a function of
+ * n = 8*H*W only; edv_op_stitch_plan (host-only, no GPU needed) writes it as an int32 table
+ * (returns the number of int32 it needs; call with plan_host = NULL to size it; negative on error,
+ * e.g. 8*H*W >= 2^24).  The caller uploads the table (plan_dev), passes n_leaves = plan[0] and a
+ * 16-byte-aligned scratch of 4*(plan[0]+plan[1]) floats. */
+long long edv_op_stitch_plan(int H, int W, int32_t* plan_host, long long cap);
+int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_dev, const int32_t* plan_dev, int n_leaves,
+                         float* scratch_dev, float* scale_shift_dev, void* stream);
 
 #ifdef __cplusplus
 }
