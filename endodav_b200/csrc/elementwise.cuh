@@ -341,19 +341,17 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __
 // Bilinear resize, align_corners=True, NHWC, 8 channels per thread.
 // (util/blocks.py:156-158; dpt_pyramid.py:90-92)
 // ---------------------------------------------------------------------------------------
+// grid.x = F*oh output rows, grid.y covers the ow*C/8 16-byte chunks of a row: 32-bit index arithmetic only
+// (the flat 64-bit div/mod chain of the first version cost more issue slots than the interpolation itself)
 template <typename T>
 __global__ void upsample_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, int F, int h, int w, int oh, int ow,
                                      int C) {
   const int c8 = C / 8;
-  const long long total = (long long)F * oh * ow * c8;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int c = (int)(i % c8) * 8;
-  long long p = i / c8;
-  int ox = (int)(p % ow);
-  long long t = p / ow;
-  int oy = (int)(t % oh);
-  int f = (int)(t / oh);
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;      // chunk within the output row
+  if (j >= ow * c8) return;
+  const int row = blockIdx.x;                               // f * oh + oy
+  const int f = row / oh, oy = row - f * oh;
+  const int ox = j / c8, c = (j - ox * c8) * 8;
   const float sy = (oh > 1) ? (float)(h - 1) / (float)(oh - 1) : 0.f;
   const float sx = (ow > 1) ? (float)(w - 1) / (float)(ow - 1) : 0.f;
   float fy = sy * oy, fx = sx * ox;
@@ -367,9 +365,9 @@ __global__ void upsample_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y,
   load_vec<T, 8>(b + ((long long)y1 * w + x0) * C, cq);
   load_vec<T, 8>(b + ((long long)y1 * w + x1) * C, d);
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * bq[j]) + ly * ((1.f - lx) * cq[j] + lx * d[j]);
-  store_vec<T, 8>(y + p * C + c, o);
+  for (int j2 = 0; j2 < 8; ++j2)
+    o[j2] = (1.f - ly) * ((1.f - lx) * a[j2] + lx * bq[j2]) + ly * ((1.f - lx) * cq[j2] + lx * d[j2]);
+  store_vec<T, 8>(y + ((long long)row * ow + ox) * C + c, o);
 }
 
 // single-channel float32 bilinear resize (align_corners=True): disparity pyramid

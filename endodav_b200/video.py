@@ -222,10 +222,11 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         # CUDA kernel (edv_op_cubic_resize_u8); ENDODAV_PREPROCESS=host keeps the reference's host path.
         # Windows are independent, so WB of them go through the network as one [WB,32,...] clip batch (the
         # engine's batched result is bit-identical to the clips run one by one, test_clip_batch_sweep_*):
-        # at 224x280 eight windows take 16.4 ms instead of 8 x 3.7 ms.
+        # at 224x280 four windows take 9.1 ms instead of 4 x 3.7 ms.
         gpu_stitch = os.environ.get("ENDODAV_STITCH", "gpu").lower() != "host"
-        # default: 8 windows at 224x280, fewer at larger network resolutions (workspace grows with WB*32 frames)
-        wb_default = max(1, min(8, int(round(8.0 * 224 * 280 / (new_h * new_w)))))
+        # default: 4 windows at 224x280 (measured best of 1/2/4/6/8 on a B200: 0.35/0.29/0.25/0.30/0.30 s for
+        # 2000 frames), fewer at larger network resolutions (the workspace grows with WB*32 frames)
+        wb_default = max(1, min(4, int(round(4.0 * 224 * 280 / (new_h * new_w)))))
         WB = max(1, int(os.environ.get("ENDODAV_WINDOW_BATCH", wb_default))) if (gpu_stitch or world > 1) else 1
         if gpu_pre:
             pinned = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]

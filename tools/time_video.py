@@ -31,6 +31,19 @@ for mode in ("gpu", "host"):
             del out
     print("infer_video_depth %d frames 256x320, preprocessing=%s: %.2f s -> %.0f frames/s (output %s)" % (n, mode, dt, n / dt, out.shape))
 
+if "--wb-sweep" in sys.argv:
+    os.environ["ENDODAV_PREPROCESS"] = "gpu"
+    for wb in (1, 2, 4, 6, 8):
+        os.environ["ENDODAV_WINDOW_BATCH"] = str(wb)
+        model.infer_video_depth(video[:400])
+        best = 1e9
+        for rep in range(3):
+            t0 = time.perf_counter()
+            model.infer_video_depth(video)
+            best = min(best, time.perf_counter() - t0)
+        print("window batch %d: %.3f s -> %.0f frames/s" % (wb, best, n / best))
+    del os.environ["ENDODAV_WINDOW_BATCH"]
+
 if "--profile" in sys.argv:
     import cProfile
     import pstats
