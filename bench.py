@@ -34,6 +34,9 @@ WORKLOADS = {
                              image_shape=(224, 280), disable_conv_head=True, residual_block_indexes=[]), (1, 8, 224, 280)),
     "vitl_518_t32": (dict(encoder="vitl", features=256, out_channels=[256, 512, 1024, 1024], r=4, lora_type="dvlora",
                           image_shape=(518, 518), disable_conv_head=True, residual_block_indexes=[]), (1, 32, 518, 518)),
+    # BASELINE config 4: ViT-L, batch of 4 x 32-frame 518x518 clips (spatial + temporal attention stress)
+    "vitl_518_t32_b4": (dict(encoder="vitl", features=256, out_channels=[256, 512, 1024, 1024], r=4, lora_type="dvlora",
+                             image_shape=(518, 518), disable_conv_head=True, residual_block_indexes=[]), (4, 32, 518, 518)),
 }
 METRIC = "frames/sec, 32-frame 518px clips"
 UNIT = "frames/s"

@@ -298,8 +298,58 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
 
             return stitch_windows(stream(), n)
 
-        # every window's disparity is written straight into this rank's (padded) slice of the gather
         per = (nwin + world - 1) // world
+        if gpu_stitch and os.environ.get("ENDODAV_GATHER", "rounds").lower() != "single":
+            # Default multi-GPU schedule: the gather to rank 0 is issued per round of WB windows per rank
+            # (asynchronously, on NCCL's stream) instead of once at the end, and rank 0 stitches round r-1 and
+            # copies its final frames to the host on a side stream while every rank computes round r.  Same
+            # collective, same data, same stitching order k = 0,1,2,... -> bit-identical result; only the
+            # serial tail (gather + 91 stitch steps + 655 MB D2H for config 3) shrinks to the last round.
+            with torch.cuda.device(dev):
+                side = torch.cuda.Stream(device=dev) if rank == 0 else None
+                st = None
+                if rank == 0:
+                    with torch.cuda.stream(side):
+                        st = _GpuStitcher(nwin, n, H, W, dev)
+                keep, works = [], []
+
+                def consume(j0, nb, bufs, work):
+                    with torch.cuda.stream(side):
+                        work.wait()                                   # side stream waits for this round's gather
+                        for s_ in range(nb):
+                            for w_ in range(world):
+                                if (j0 + s_) * world + w_ < nwin:
+                                    st.push(bufs[w_][s_])
+
+                prev = None
+                for j0 in range(0, per, WB):
+                    nb = min(WB, per - j0)
+                    have = max(0, min(nb, len(mine) - j0))             # real windows of this rank in the round
+                    send = torch.empty(nb, INFER_LEN, H, W, dtype=torch.float32, device=dev)
+                    if have:
+                        launch(j0, have, send[:have].view(have * INFER_LEN, H, W))
+                    if have < nb:
+                        send[have:].zero_()
+                    bufs = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+                    work = dist.gather(send, bufs, dst=0, async_op=True)
+                    keep.append((send, bufs))
+                    works.append(work)
+                    if rank == 0:
+                        if prev is not None:
+                            consume(*prev)
+                        prev = (j0, nb, bufs, work)
+                if rank == 0:
+                    consume(*prev)
+                    with torch.cuda.stream(side):
+                        result = st.finish()
+                    torch.cuda.current_stream().synchronize()
+                    return result
+                for work in works:
+                    work.wait()
+                torch.cuda.current_stream().synchronize()
+                return None
+        # ENDODAV_GATHER=single: every window's disparity is written straight into this rank's (padded) slice of
+        # ONE gather issued after the last window
         with torch.cuda.device(dev):
             local_t = torch.empty(per, INFER_LEN, H, W, dtype=torch.float32, device=dev)
             for j in range(0, len(mine), WB):

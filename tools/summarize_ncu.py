@@ -72,7 +72,7 @@ def full(src, dst):
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
-    ours = re.compile(r"gemm_tc|flash_attention|temporal_attention|head_fused|conv3x3_halo|layernorm_kernel|groupnorm|upsample_nhwc|preprocess_patches")
+    ours = re.compile(r"gemm_tc|flash_attention|temporal_attention|head_fused|conv3x3_halo|layernorm_kernel|groupnorm|upsample_nhwc|preprocess_patches|stitch_")
     data = [d for d in data if ours.search(d[ki])]   # drop torch's own fill / RNG kernels from the captured range
     # DRAM traffic per launch, keyed by bench.py's call-site names (one profiled launch per op, in OPS order)
     traffic = {}
@@ -85,8 +85,11 @@ def full(src, dst):
         with open(dst.replace(".txt", "_traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
     with open(dst, "w") as f:
-        f.write("# ncu --set full --clock-control none --profile-from-start off ; source: %s\n" % src)
-        f.write("# one warm launch per op of `tools/prof_ops.py --range` (ops in order: %s)\n" % " ".join(OPS))
+        if len(sys.argv) > 4:
+            f.write("# ncu --set full --clock-control none ; source: %s\n# %s\n" % (src, sys.argv[4]))
+        else:
+            f.write("# ncu --set full --clock-control none --profile-from-start off ; source: %s\n" % src)
+            f.write("# one warm launch per op of `tools/prof_ops.py --range` (ops in order: %s)\n" % " ".join(OPS))
         for d in data:
             f.write("\n== %s\n" % short(d[ki]))
             for w in WANT:
