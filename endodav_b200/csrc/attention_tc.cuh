@@ -329,21 +329,11 @@ void launch_attention_tc(edv::Launch& L, int dtype, const void* qkv, void* out, 
   uint64_t str[1] = {(uint64_t)3 * D * 2};
   uint32_t box[2] = {(uint32_t)FA_HD, (uint32_t)FA_BM};
   if (!make_map(L, &tm, dtype, qkv, 2, dims, str, box, 128)) return;
-  // EDV_FA_POLY=<0|2|3|4>: every n-th exponential on the FMA pipe (tuning knob; 0 = all MUFU)
-  static int pm = -1;
-  if (pm < 0) {
-    const char* env = getenv("EDV_FA_POLY");
-    pm = env ? atoi(env) : FA_POLY_DEFAULT;
-    if (pm != 0 && pm != 2 && pm != 3 && pm != 4) pm = FA_POLY_DEFAULT;
-  }
-  void (*kern)(const CUtensorMap, T*, int, int) = pm == 0 ? flash_attention_tc_kernel<T, 0>
-                                                  : pm == 2 ? flash_attention_tc_kernel<T, 2>
-                                                  : pm == 3 ? flash_attention_tc_kernel<T, 3>
-                                                            : flash_attention_tc_kernel<T, 4>;
-  static bool attr_done[5] = {false, false, false, false, false};
-  if (!attr_done[pm]) {
+  auto kern = flash_attention_tc_kernel<T, FA_POLY_DEFAULT>;
+  static bool attr_done = false;
+  if (!attr_done) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM);
-    attr_done[pm] = true;
+    attr_done = true;
   }
   dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, F);
   kern<<<grid, FA_THREADS, FA_SMEM, L.stream>>>(tm, (T*)out, S, heads);

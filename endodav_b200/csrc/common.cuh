@@ -235,3 +235,8 @@ __device__ __forceinline__ void epi_apply(const Epi& e, long long m, long long o
     store_vec<T, NV>((T*)e.out_relu + orow * e.ldo + ocol, r);
   }
 }
+
+// compile-time epilogue kinds of the tcgen05 GEMM (gemm_tc.cuh); Epi::kind holds one of these masks or -1
+namespace tc {
+enum { EF_BIAS = 1, EF_GELU = 2, EF_RELU = 4, EF_RES1_F32 = 8, EF_RES1_T = 16, EF_RES2_T = 32, EF_OUT_F32 = 64, EF_OUT_RELU = 128, EF_ROWBIAS = 256 };
+}

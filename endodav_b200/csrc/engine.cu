@@ -29,6 +29,7 @@ struct WeightRef {
 struct Buf {
   size_t off = 0;
   size_t bytes = 0;
+  int elem = 0;   // element size in bytes (4: float32 regardless of the activation dtype; 8: float2 statistics)
 };
 
 struct DebugTap {
@@ -371,7 +372,7 @@ struct Fwd {
       if (g.res_blocks & (1 << i)) res_block(n, x);
       if (i == 0) snapshot("block0", x, true, p.M, D, D);
       if (tap_i < 4 && i == g.taps[tap_i]) {
-        char tn[8];
+        char tn[16];
         snprintf(tn, sizeof tn, "tap%d", tap_i);
         // final norm on the tap + cls split (vision_transformer.py:318-321)
         layernorm(L, dt, x, wf("norm.w", D), wf("norm.b", D), buf(tn), p.Mp, D, 1e-6f, p.N, 1);
@@ -532,6 +533,8 @@ int set_err(edv_ctx* c, int code, const char* fmt, ...) {
 // =========================================================================================
 extern "C" {
 
+int edv_abi_version(void) { return EDV_ABI_VERSION; }
+
 int edv_create(const edv_config* cfg, edv_ctx** out) {
   if (!cfg || !out) return set_err(nullptr, EDV_ERR_ARG, "edv_create: null argument");
   *out = nullptr;
@@ -623,16 +626,17 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
 
   const size_t es = dtype_size(g.dtype);
   size_t off = 0;
-  auto add = [&](const char* name, size_t bytes) {
+  auto add = [&](const char* name, size_t bytes, int elem = 0) {
     Buf b;
     b.off = off;
     b.bytes = bytes;
+    b.elem = elem ? elem : (int)es;
     p.bufs[name] = b;
     off += (bytes + 1023) & ~(size_t)1023;
   };
   const int D = g.dim;
   add("A0", (size_t)p.Mp * KPATCH * es);
-  add("x", (size_t)p.M * D * 4);
+  add("x", (size_t)p.M * D * 4, 4);
   add("xn", (size_t)p.M * D * es);
   add("qkv", (size_t)p.M * 3 * D * es);
   add("ao", (size_t)p.M * D * es);
@@ -671,9 +675,9 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
     mm8 = std::max(mm8, rows * 8 * C);
   }
   if (!g.no_motion) {
-    add("mm.stats", (size_t)p.BT * 32 * (1 + GN_MAX_SPLIT) * sizeof(float2));
+    add("mm.stats", (size_t)p.BT * 32 * (1 + GN_MAX_SPLIT) * sizeof(float2), 8);
     add("mm.gn", mmC * es);
-    add("mm.hs", mmC * 4);
+    add("mm.hs", mmC * 4, 4);
     add("mm.ln", mmC * es);
     add("mm.qkv", mm3 * es);
     add("mm.att", mmC * es);
@@ -704,7 +708,7 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
   for (int s = 0; s < 4; ++s) {
     char n[8];
     snprintf(n, sizeof n, "disp%d", s);
-    add(n, (size_t)p.BT * p.out_h[s] * p.out_w[s] * 4);
+    add(n, (size_t)p.BT * p.out_h[s] * p.out_w[s] * 4, 4);
   }
   if (ctx->debug) {
     auto tap = [&](const char* name, long long rows, int cols) {
@@ -781,6 +785,21 @@ int edv_debug_tap(edv_ctx* ctx, const char* name, size_t* offset_bytes, long lon
   *offset_bytes = it->second.buf.off;
   *rows = it->second.rows;
   *cols = it->second.cols;
+  return EDV_OK;
+}
+
+// Enumerate the named workspace buffers of the current plan (range / saturation checks of the 16-bit
+// intermediates: the Python host views its own workspace tensor at `offset_bytes`).  Returns EDV_ERR_ARG
+// past the last buffer.
+int edv_plan_buffer(edv_ctx* ctx, int index, char* name, int name_cap, size_t* offset_bytes, size_t* bytes, int* elem_bytes) {
+  if (!ctx || !ctx->plan.valid || index < 0 || !name || name_cap < 1 || !offset_bytes || !bytes || !elem_bytes) return EDV_ERR_ARG;
+  if (index >= (int)ctx->plan.bufs.size()) return EDV_ERR_ARG;
+  auto it = ctx->plan.bufs.begin();
+  std::advance(it, index);
+  snprintf(name, name_cap, "%s", it->first.c_str());
+  *offset_bytes = it->second.off;
+  *bytes = it->second.bytes;
+  *elem_bytes = it->second.elem;
   return EDV_OK;
 }
 

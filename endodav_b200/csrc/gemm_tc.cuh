@@ -69,7 +69,7 @@ template <typename T> __device__ __forceinline__ float4 ld4_as_f32(const void* p
 // (ncu: stall_no_inst on every other line, ~2 500 cycles per 32-column chunk).  The hot call sites
 // of the forward therefore get straight-line instantiations (F >= 0: bit mask below); anything
 // else (row-bias tables, pixel shuffle, sigmoid) runs the generic F = -1 version.
-enum { EF_BIAS = 1, EF_GELU = 2, EF_RELU = 4, EF_RES1_F32 = 8, EF_RES1_T = 16, EF_RES2_T = 32, EF_OUT_F32 = 64, EF_OUT_RELU = 128, EF_ROWBIAS = 256 };
+// (the EF_* bit mask is declared in common.cuh: the launcher side needs it without the kernels)
 
 // The fused epilogue on NS row segments (4 consecutive columns starting at n of rows mm[it] ->
 // output rows oo[it], oo < 0 = masked).  Same order of operations as epi_apply (common.cuh):

@@ -16,9 +16,11 @@ DTYPES = {"fp32": EDV_F32, "f32": EDV_F32, "float32": EDV_F32, "bf16": EDV_BF16,
           "fp16": EDV_F16, "f16": EDV_F16, "float16": EDV_F16}
 TORCH_DTYPE = {EDV_F32: torch.float32, EDV_BF16: torch.bfloat16, EDV_F16: torch.float16}
 
+ABI_VERSION = 3   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
+
 EXPORTS = [
-    "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
-    "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_op_linear", "edv_op_conv3x3",
+    "edv_abi_version", "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
+    "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_plan_buffer", "edv_op_linear", "edv_op_conv3x3",
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
     "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
     "edv_op_disp_head", "edv_op_cubic_resize_u8", "edv_op_stitch_window", "edv_op_stitch_plan",
@@ -52,6 +54,10 @@ def load_library():
             "endodav_b200: %s is missing -- build it with `python -m endodav_b200.build` "
             "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
+    if not hasattr(lib, "edv_abi_version") or lib.edv_abi_version() != ABI_VERSION:
+        got = lib.edv_abi_version() if hasattr(lib, "edv_abi_version") else "none"
+        raise EndoDAVError("endodav_b200: %s is stale (ABI version %s, this host expects %d) -- rebuild it with "
+                           "`python -m endodav_b200.build --force`" % (LIB_PATH, got, ABI_VERSION))
     vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
     lib.edv_create.argtypes = [ctypes.POINTER(EdvConfig), ctypes.POINTER(vp)]
     lib.edv_destroy.argtypes = [vp]
@@ -67,6 +73,7 @@ def load_library():
     lib.edv_set_debug.argtypes = [vp, ci]
     lib.edv_debug_tap.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_longlong),
                                   ctypes.POINTER(ci)]
+    lib.edv_plan_buffer.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(sz), ctypes.POINTER(sz), ctypes.POINTER(ci)]
     lib.edv_profile.argtypes = [vp, ci]
     lib.edv_profile_reset.argtypes = [vp]
     lib.edv_profile_collect.argtypes = [vp]
@@ -213,6 +220,22 @@ class Engine:
             out.append(dict(name=buf.value.decode(), ms=ms.value, count=cnt.value, flops=fl.value, bytes=by.value))
         return out
 
+    def plan_buffers(self):
+        """-> {name: tensor view into the workspace} for every buffer of the current plan (16-bit buffers in the
+        compute dtype, float32 / float2 ones as float32).  Diagnostic: range scans of the intermediates."""
+        out = {}
+        buf = ctypes.create_string_buffer(64)
+        base = self._ws_ptr() - self.workspace.data_ptr()
+        i = 0
+        while True:
+            off, nb, el = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_int(0)
+            if self.lib.edv_plan_buffer(self.ctx, i, buf, 64, ctypes.byref(off), ctypes.byref(nb), ctypes.byref(el)) != 0:
+                break
+            dt = TORCH_DTYPE[self.cfg.dtype] if el.value == 2 else torch.float32
+            out[buf.value.decode()] = self.workspace[base + off.value: base + off.value + nb.value].view(dt)
+            i += 1
+        return out
+
     def debug_tap(self, name):
         off, rows, cols = ctypes.c_size_t(0), ctypes.c_longlong(0), ctypes.c_int(0)
         _check(self.lib.edv_debug_tap(self.ctx, name.encode(), ctypes.byref(off), ctypes.byref(rows), ctypes.byref(cols)),
@@ -327,10 +350,18 @@ def stitch_plan(H, W):
     return plan
 
 
-def op_stitch_window(win, k, out, plan_dev, n_leaves, scratch, scale_shift):
-    """Append window k ([32,H,W] float32, device) to the stitched sequence ``out`` ([32+22*(nwin-1),H,W]) on the
-    current stream: the reference's scale/shift alignment + cross-fade (endodav.py:213-254), no host sync."""
+def op_stitch_window(win, k, out, plan_dev, n_leaves, scratch, scale_shift, base_frame=0):
+    """Append window k ([32,H,W] float32, device) to the stitched sequence on the current stream: the reference's
+    scale/shift alignment + cross-fade (endodav.py:213-254), no host sync.  ``out[i]`` holds frame
+    ``base_frame + i`` of the sequence (base_frame = 0: ``out`` is the whole [32+22*(nwin-1),H,W] sequence); window k
+    touches frames [10+22k-8, 10+22k+22), which must lie inside ``out``."""
     lib = load_library()
     _, H, W = win.shape
-    _check(lib.edv_op_stitch_window(_ptr(win), int(k), H, W, _ptr(out), _ptr(plan_dev), int(n_leaves), _ptr(scratch),
+    lo = 0 if k == 0 else 10 + 22 * k - 8
+    hi = 32 if k == 0 else 10 + 22 * k + 22
+    if lo < base_frame or hi - base_frame > out.shape[0]:
+        raise EndoDAVError("op_stitch_window: window %d touches frames [%d,%d) outside the buffer [%d,%d)"
+                           % (k, lo, hi, base_frame, base_frame + out.shape[0]))
+    out_ptr = ctypes.c_void_p(out.data_ptr() - base_frame * H * W * 4)
+    _check(lib.edv_op_stitch_window(_ptr(win), int(k), H, W, out_ptr, _ptr(plan_dev), int(n_leaves), _ptr(scratch),
                                     _ptr(scale_shift), _stream()), None, "edv_op_stitch_window")

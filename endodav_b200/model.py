@@ -292,7 +292,34 @@ class endodav(nn.Module):
         return self.state_dict()
 
     def _versions(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        # (storage pointer, in-place version counter) of every parameter / buffer.  The tensor list is cached: walking
+        # ~300 holder modules costs more than a 224x280 forward; `_apply` (.cuda() / .to()) and load_state_dict reset it.
+        ts = self.__dict__.get("_tensor_cache")
+        if ts is None:
+            ts = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_tensor_cache"] = ts
+        return tuple((p.data_ptr(), p._version) for p in ts)
+
+    def invalidate_weights(self):
+        """Force a re-pack of the weights on the next forward.
+
+        Re-packing is triggered automatically by ``load_state_dict``, by ``.to()`` / ``.cuda()`` and by in-place
+        parameter updates that bump the autograd version counter (``p.add_(...)``, ``p.copy_(...)``, optimiser steps).
+        Writes through ``p.data`` (``p.data.copy_(w)``, ``p.data += ...`` -- the idiom of the reference's LoRA merge code)
+        bump neither the counter nor the pointer: call this method after them."""
+        self._packed_versions = None
+        self.__dict__["_tensor_cache"] = None
+        return self
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.invalidate_weights()
+        return out
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.invalidate_weights()
+        return out
 
     def _device(self):
         return next(self.parameters()).device

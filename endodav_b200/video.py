@@ -149,15 +149,27 @@ class _GpuStitcher:
     """Device-side replacement of ``stitch_windows`` (endodav.py:213-254): windows are pushed in order, each
     one is aligned and cross-faded by ``edv_op_stitch_window`` on the current stream (no host sync), and the
     frames it makes final are copied asynchronously into the pinned host array that ``finish`` returns
-    (float32 [n_frames,H,W]; torch's pinned-memory cache recycles it once the caller drops it)."""
+    (float32 [n_frames,H,W]; torch's pinned-memory cache recycles it once the caller drops it).
 
-    def __init__(self, n_windows, n_frames, H, W, device):
+    Device memory is bounded: only a segment of ``8 + 22*chunk`` frames of the stitched sequence lives on the
+    GPU (frames older than the 8-frame cross-fade tail are final and already on their way to the host); when
+    a window would run past the segment, the tail is moved to its start.  ``edv_op_stitch_window`` addresses
+    the sequence from a base pointer, so the segment is presented to it through a shifted (virtual) base."""
+
+    SEGMENT_BYTES = 256 << 20
+
+    def __init__(self, n_windows, n_frames, H, W, device, plan=None):
         from . import engine as _engine
 
         self._op = _engine.op_stitch_window
         self.nwin, self.n, self.k = n_windows, n_frames, 0
-        self.seq = torch.empty(INFER_LEN + STEP * (n_windows - 1), H, W, dtype=torch.float32, device=device)
-        plan = _engine.stitch_plan(H, W)       # numpy's pairwise-sum tree for the 8*H*W overlap elements
+        self.hw = H * W
+        chunk = max(1, min(n_windows, self.SEGMENT_BYTES // (STEP * H * W * 4)))
+        self.cap = max(INFER_LEN, INTERP_LEN + STEP * chunk)
+        self.seg = torch.empty(self.cap, H, W, dtype=torch.float32, device=device)
+        self.base = 0                          # global frame index of seg[0]
+        if plan is None:
+            plan = _engine.stitch_plan(H, W)   # numpy's pairwise-sum tree for the 8*H*W overlap elements
         self.n_leaves = int(plan[0])
         self.plan = torch.from_numpy(plan).to(device)
         self.scratch = torch.empty(4 * int(plan[0] + plan[1]), dtype=torch.float32, device=device)
@@ -167,16 +179,33 @@ class _GpuStitcher:
     def push(self, win):
         """win: [32,H,W] float32 device tensor = window ``self.k`` resized to the frame size."""
         k = self.k
-        self._op(win, k, self.seq, self.plan, self.n_leaves, self.scratch, self.scale_shift)
+        if k > 0:
+            pos = INFER_LEN + STEP * (k - 1)                       # frames aligned so far
+            if pos + STEP - self.base > self.cap:                  # would run past the segment: move the tail to its start
+                tail = self.seg[pos - INTERP_LEN - self.base: pos - self.base].clone()
+                self.seg[:INTERP_LEN].copy_(tail)
+                self.base = pos - INTERP_LEN
+        self._op(win, k, self.seg, self.plan, self.n_leaves, self.scratch, self.scale_shift, base_frame=self.base)
         self.k += 1
         lo, hi = final_frame_range(k, self.nwin, self.n)
         if hi > lo:
-            self.out[lo:hi].copy_(self.seq[lo:hi], non_blocking=True)
+            self.out[lo:hi].copy_(self.seg[lo - self.base: hi - self.base], non_blocking=True)
 
     def finish(self):
         assert self.k == self.nwin
         torch.cuda.current_stream().synchronize()
         return self.out.numpy()
+
+
+def _stitch_plan_or_none(H, W):
+    """The on-GPU stitching needs 8*H*W < 2^24 (np.sum(ones) must stay exact in float32, edv_op_stitch_plan);
+    larger frames (>= ~2.1 MP: 2048x1080, 4K) use the reference's numpy chain on the host instead."""
+    from . import engine as _engine
+
+    try:
+        return _engine.stitch_plan(H, W)
+    except _engine.EndoDAVError:
+        return None
 
 
 def _dist():
@@ -216,6 +245,10 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         from . import engine as _engine
 
         gpu_pre = os.environ.get("ENDODAV_PREPROCESS", "gpu").lower() != "host"
+        if frames.dtype != np.uint8:
+            # the reference accepts any dtype through ``.astype(np.float32) / 255`` (endodav.py:195); the GPU cubic
+            # resize is written for uint8 frames, so other dtypes take the reference's host preprocessing path
+            gpu_pre = False
         # two pinned staging buffers: the host fills window j+1 while the GPU runs window j.
         # gpu_pre (default): the raw uint8 frames of the window are uploaded (4x fewer bytes than the
         # resized float clip) and the reference's /255 + cv2 INTER_CUBIC resize + HWC->CHW runs in a
@@ -224,14 +257,19 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         # engine's batched result is bit-identical to the clips run one by one, test_clip_batch_sweep_*):
         # at 224x280 four windows take 9.1 ms instead of 4 x 3.7 ms.
         gpu_stitch = os.environ.get("ENDODAV_STITCH", "gpu").lower() != "host"
+        splan = _stitch_plan_or_none(H, W) if gpu_stitch else None
+        if splan is None:
+            gpu_stitch = False
         # default: 4 windows at 224x280 (measured best of 1/2/4/6/8 on a B200: 0.35/0.29/0.25/0.30/0.30 s for
         # 2000 frames), fewer at larger network resolutions (the workspace grows with WB*32 frames)
         wb_default = max(1, min(4, int(round(4.0 * 224 * 280 / (new_h * new_w)))))
         WB = max(1, int(os.environ.get("ENDODAV_WINDOW_BATCH", wb_default))) if (gpu_stitch or world > 1) else 1
         if gpu_pre:
-            pinned = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            # the staging buffers hold raw frames: bound them by the FRAME size too (256 MB each; 1080p -> one window)
+            WB = max(1, min(WB, (256 << 20) // (INFER_LEN * H * W * 3)))
+            pinned = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
         else:
-            pinned = [torch.empty(WB, INFER_LEN, 3, new_h, new_w, dtype=torch.float32).pin_memory() for _ in range(2)]
+            pinned = [torch.empty(WB, INFER_LEN, 3, new_h, new_w, dtype=torch.float32, pin_memory=True) for _ in range(2)]
         copied = [None, None]
         calls = [0]
 
@@ -265,7 +303,7 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
             # (edv_op_stitch_window, no host sync); the frames a window makes final are copied back through a
             # small pinned ring while the next windows run.
             with torch.cuda.device(dev):
-                st = _GpuStitcher(nwin, n, H, W, dev)
+                st = _GpuStitcher(nwin, n, H, W, dev, splan)
                 for j in range(0, nwin, WB):
                     nb = min(WB, nwin - j)
                     d = launch(j, nb).view(nb, INFER_LEN, H, W)
@@ -277,7 +315,7 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
             # (strictly sequential, host-side) stitching, and every result comes back through a small
             # ring of pinned buffers, so GPU work, D2H copies and the numpy stitching overlap.
             AHEAD, RING = 2, 3
-            ring = [torch.empty(INFER_LEN, H, W, dtype=torch.float32).pin_memory() for _ in range(RING)]
+            ring = [torch.empty(INFER_LEN, H, W, dtype=torch.float32, pin_memory=True) for _ in range(RING)]
             done = [None] * RING
 
             def stream():
@@ -310,8 +348,8 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                 st = None
                 if rank == 0:
                     with torch.cuda.stream(side):
-                        st = _GpuStitcher(nwin, n, H, W, dev)
-                keep, works = [], []
+                        st = _GpuStitcher(nwin, n, H, W, dev, splan)
+                inflight = []      # (send, bufs, work) of rounds whose gather may still be running
 
                 def consume(j0, nb, bufs, work):
                     with torch.cuda.stream(side):
@@ -320,6 +358,8 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                             for w_ in range(world):
                                 if (j0 + s_) * world + w_ < nwin:
                                     st.push(bufs[w_][s_])
+                        for b_ in bufs:
+                            b_.record_stream(side)          # freed by the caller below: keep the memory until the side stream is done
 
                 prev = None
                 for j0 in range(0, per, WB):
@@ -332,19 +372,22 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                         send[have:].zero_()
                     bufs = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
                     work = dist.gather(send, bufs, dst=0, async_op=True)
-                    keep.append((send, bufs))
-                    works.append(work)
+                    inflight.append((send, bufs, work))
                     if rank == 0:
                         if prev is not None:
                             consume(*prev)
                         prev = (j0, nb, bufs, work)
+                    # rounds older than the previous one are finished with: release their buffers (a whole video's
+                    # worth of gather buffers would otherwise stay allocated on rank 0 until the end)
+                    while len(inflight) > 2:
+                        inflight.pop(0)[2].wait()
                 if rank == 0:
                     consume(*prev)
                     with torch.cuda.stream(side):
                         result = st.finish()
                     torch.cuda.current_stream().synchronize()
                     return result
-                for work in works:
+                for _, _, work in inflight:
                     work.wait()
                 torch.cuda.current_stream().synchronize()
                 return None
@@ -381,7 +424,7 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         return None
     if forward_window is None and gpu_stitch:
         with torch.cuda.device(local_t.device):
-            st = _GpuStitcher(nwin, n, H, W, local_t.device)
+            st = _GpuStitcher(nwin, n, H, W, local_t.device, splan)
             for k in range(nwin):
                 st.push(gathered[k % world][k // world])
             return st.finish()

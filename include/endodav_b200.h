@@ -27,6 +27,12 @@ extern "C" {
 
 typedef struct edv_ctx edv_ctx;
 
+/* Bumped whenever an entry point's argument list or a struct layout changes.  The ctypes host
+ * (endodav_b200/engine.py) mirrors the signatures by hand, so it refuses a library whose
+ * edv_abi_version() differs from its own constant instead of calling it with a stale layout. */
+#define EDV_ABI_VERSION 3
+int edv_abi_version(void);
+
 enum edv_status {
   EDV_OK = 0,
   EDV_ERR_ARG = -1,      /* bad argument / unsupported shape */
@@ -119,6 +125,11 @@ int edv_profile_get(edv_ctx* ctx, int index, char* name, int name_cap, double* m
  * caller's workspace; edv_debug_tap returns where. */
 int edv_set_debug(edv_ctx* ctx, int on);
 int edv_debug_tap(edv_ctx* ctx, const char* name, size_t* offset_bytes, long long* rows, int* cols);
+
+/* Enumerate the named workspace buffers of the current plan: index 0,1,... until EDV_ERR_ARG.  elem_bytes is 2
+ * for 16-bit activations, 4 for float32 buffers (residual stream, disparities), 8 for float2 statistics.  Used by
+ * the fp16 range / saturation tests (tests/test_gpu_fullsize.py) to scan every intermediate for inf / near-overflow. */
+int edv_plan_buffer(edv_ctx* ctx, int index, char* name, int name_cap, size_t* offset_bytes, size_t* bytes, int* elem_bytes);
 
 /* --- per-kernel entry points (unit parity tests + ncu) ---------------------------------- */
 

@@ -43,6 +43,16 @@ FORWARD_CASES = {
     "fwd_vitl": (dict(encoder="vitl", lora_type="dvlora"), (70, 84), (1, 2, 70, 84), 61, 62),
 }
 
+# Full-size BASELINE configurations (2: ViT-S 32 x 518 x 518; 4: ViT-L at 518 x 518, two frames): the reference output
+# is stored as a strided sample (frames FULL_FRAMES, every FULL_STRIDE-th pixel) so the fixture stays small; it pins the
+# oracle at S = 1370 tokens / T = 32 / 37x37 -> 19x19 maps, and the GPU tests compare the CUDA path with the oracle on
+# the full maps.  name -> (ctor overrides, image_shape, input, weight seed, frame seed, frames kept)
+FULL_CASES = {
+    "full_vits_518_t32": (dict(encoder="vits", lora_type="dvlora"), (518, 518), (1, 32, 518, 518), 1234, 4321, [0, 15, 31]),
+    "full_vitl_518_t2": (dict(encoder="vitl", lora_type="dvlora"), (518, 518), (1, 2, 518, 518), 61, 62, [0, 1]),
+}
+FULL_STRIDE = 7
+
 VIDEO_CASES = {
     # name -> (N, H, W, image_shape, weight seed, frame seed)
     "video_n45": (45, 48, 64, (28, 42), 1234, 7),
@@ -131,6 +141,28 @@ def _dash_past_warmup(model):
             m.FLAG = m.warmup + 1
 
 
+def make_fullsize(manifest):
+    import time
+    for name, (over, ishape, (B, T, H, W), wseed, fseed, keep) in FULL_CASES.items():
+        kw = ctor_kwargs(over, ishape)
+        sd = weights.make_state_dict(oracle_cfg(kw), wseed)
+        model = ref_import.build_reference_model(kw)
+        model.load_state_dict(sd, strict=True)
+        x = weights.make_frames(B, T, H, W, fseed)
+        t0 = time.time()
+        with torch.no_grad():
+            out = model(x)
+        d0 = out[("disp", 0)].numpy().astype(np.float32)
+        arrays = {"disp0": d0[keep][:, :, ::FULL_STRIDE, ::FULL_STRIDE].copy(),
+                  "disp3": out[("disp", 3)].numpy().astype(np.float32)[keep].copy(),
+                  "stats": np.array([d0.mean(), d0.std(), d0.min(), d0.max()], dtype=np.float64)}
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
+        manifest[name] = dict(kind="forward_full", ctor={k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()},
+                              input=[B, T, H, W], weight_seed=wseed, frame_seed=fseed, frames=keep, stride=FULL_STRIDE)
+        print(name, {k: v.shape for k, v in arrays.items()}, arrays["stats"], "%.1f s" % (time.time() - t0))
+        del model, out
+
+
 def stub_forward(x):
     """Deterministic stand-in network used for the bit-exact index/stitch fixtures: per-frame
     disparity = channel mean + 0.1*frame-mean, so every slot's source frame is identifiable."""
@@ -144,6 +176,13 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref_mod = ref_import.import_reference()
     manifest = {}
+    if "--fullsize-only" in sys.argv:  # add the full-size fixtures without regenerating the others
+        with open(os.path.join(GOLDEN_DIR, "manifest.json")) as f:
+            manifest = json.load(f)
+        make_fullsize(manifest)
+        with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
+            json.dump(manifest, f, indent=1)
+        return
     if "--endodac-only" in sys.argv:   # add the endodac fixtures without regenerating the others
         with open(os.path.join(GOLDEN_DIR, "manifest.json")) as f:
             manifest = json.load(f)
@@ -208,6 +247,7 @@ def main():
     manifest["video_stub"] = dict(kind="video_stub", n=STUB_VIDEO_N, input=[30, 44], image_shape=[28, 42])
 
     make_endodac(manifest)
+    make_fullsize(manifest)
 
     with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)

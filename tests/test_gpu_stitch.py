@@ -102,3 +102,75 @@ def test_infer_video_depth_gpu_stitch_equals_host_stitch(monkeypatch):
     b = model.infer_video_depth(v)
     assert a.shape == b.shape == arrays["depth"].shape
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("seg_bytes", [1, 22 * 30 * 44 * 4 * 3])
+def test_stitch_bounded_device_segment_is_bit_exact(monkeypatch, seg_bytes):
+    """The stitched sequence lives on the GPU only as a sliding segment (long HD videos must not keep
+    N*H*W*4 bytes on the device).  Forcing the smallest segments (1 and 3 windows) must not change a single bit."""
+    n, H, W = 230, 30, 44
+    nwin = V.num_windows(n)
+    wins = _windows(nwin, H, W, 17)
+    ref = V.stitch_windows(wins, n)
+    monkeypatch.setattr(V._GpuStitcher, "SEGMENT_BYTES", seg_bytes)
+    got, _ = _gpu_stitch(wins, n)
+    assert np.array_equal(got, ref)
+
+
+def test_large_frames_fall_back_to_host_stitching():
+    """8*H*W >= 2^24 (2048 x 1024 frames): edv_op_stitch_plan refuses the shape and infer_video_depth must run the
+    reference's numpy chain instead of raising."""
+    import endodav_b200 as E
+
+    assert V._stitch_plan_or_none(1024, 2048) is None and V._stitch_plan_or_none(256, 320) is not None
+    kw = dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
+              image_shape=(28, 56), disable_conv_head=True, residual_block_indexes=[])
+    model = E.endodav(dtype="fp16", **kw)
+    from endodav_b200 import synthetic
+    synthetic.randomize_(model, 5)
+    model = model.cuda().eval()
+    v = weights.make_video_u8(24, 1024, 2048, 3)
+    out = model.infer_video_depth(v)
+    assert out.shape == (24, 1024, 2048) and out.dtype == np.float32 and np.isfinite(out).all()
+
+
+def test_non_uint8_frames_take_the_host_preprocessing_path():
+    """The reference accepts any frame dtype through .astype(np.float32)/255 (endodav.py:195)."""
+    import endodav_b200 as E
+    from golden_util import oracle_cfg
+
+    m, arrays = load_case("video_n5")
+    kw = dict(m["ctor"])
+    kw["image_shape"] = tuple(kw["image_shape"])
+    model = E.endodav(dtype="fp32", **kw)
+    model.load_state_dict(weights.make_state_dict(oracle_cfg(m["ctor"]), m["weight_seed"]), strict=True)
+    model = model.cuda().eval()
+    N, H, W = m["input"]
+    v = weights.make_video_u8(N, H, W, m["frame_seed"])
+    a = model.infer_video_depth(v.astype(np.int32))
+    err = np.abs(a - arrays["depth"]) / np.maximum(np.abs(arrays["depth"]), 1.0)
+    assert err.max() <= 5e-4
+
+
+def test_data_writes_need_invalidate_weights():
+    """writes through .data bump neither the version counter nor the pointer; invalidate_weights()
+    forces the re-pack, in-place ops and load_state_dict trigger it by themselves."""
+    import endodav_b200 as E
+    from endodav_b200 import synthetic
+
+    kw = dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
+              image_shape=(28, 42), disable_conv_head=True, residual_block_indexes=[])
+    model = E.endodav(dtype="fp16", **kw)
+    synthetic.randomize_(model, 7)
+    model = model.cuda().eval()
+    x = weights.make_frames(1, 2, 28, 42, 3).cuda()
+    a = model(x)[("disp", 0)].clone()
+    p = dict(model.named_parameters())["head.scratch.output_conv2.0.bias"]
+    p.data.add_(0.25)                                   # invisible to the automatic check
+    model.invalidate_weights()
+    b = model(x)[("disp", 0)].clone()
+    assert not torch.equal(a, b)
+    with torch.no_grad():
+        p.add_(0.25)                                    # bumps _version: picked up automatically
+    c = model(x)[("disp", 0)]
+    assert not torch.equal(b, c)

@@ -33,6 +33,33 @@ def test_forward_matches_reference_golden(name):
     assert float(np.abs(arrays["disp0"]).mean()) > 0.05  # not the degenerate all-zero output
 
 
+FULL = [k for k, v in manifest().items() if v["kind"] == "forward_full"]
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_forward_full_size_matches_reference_golden(name):
+    """BASELINE configs 2 and 4 at their real resolution (S = 1370 tokens, 37x37 -> 19x19 maps, T = 32 for ViT-S):
+    the oracle against a strided sample of the UNMODIFIED reference's output (oracle/make_golden.py FULL_CASES)."""
+    m, arrays = load_case(name)
+    ctor = m["ctor"]
+    cfg = oracle_cfg(ctor)
+    sd = weights.make_state_dict(cfg, m["weight_seed"])
+    B, T, H, W = m["input"]
+    x = weights.make_frames(B, T, H, W, m["frame_seed"])
+    with torch.no_grad():
+        out = orc.forward(sd, x, cfg, tuple(ctor["image_shape"]))
+    d0 = out[("disp", 0)].numpy()
+    st = m["stride"]
+    got = d0[m["frames"]][:, :, ::st, ::st]
+    assert got.shape == arrays["disp0"].shape
+    assert np.abs(got - arrays["disp0"]).max() <= ATOL, float(np.abs(got - arrays["disp0"]).max())
+    got3 = out[("disp", 3)].numpy()[m["frames"]]
+    assert np.abs(got3 - arrays["disp3"]).max() <= ATOL
+    stats = arrays["stats"]
+    assert abs(float(d0.mean()) - stats[0]) <= 1e-5 and abs(float(d0.std()) - stats[1]) <= 1e-5
+    assert stats[1] > 0.1   # non-degenerate
+
+
 def test_unmerged_lora_equals_merged():
     m, arrays = load_case("fwd_vits_dvlora")
     cfg = oracle_cfg(m["ctor"])

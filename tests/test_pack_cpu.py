@@ -116,3 +116,30 @@ def test_pack_dtypes_and_alignment():
                 assert v.shape[0] % 32 == 0, (k, v.shape)   # N of every GEMM is a multiple of 32
             else:
                 assert v.dtype == torch.float32, k
+
+
+def test_weight_invalidation_hooks():
+    """load_state_dict / .to() / invalidate_weights() drop the packed-weight key so the next forward re-packs;
+    the cached tensor list follows the module's current parameters (model.py)."""
+    import endodav_b200 as E
+
+    model = E.endodav(encoder="vits", features=64, out_channels=[48, 96, 192, 384], lora_type="dvlora", image_shape=(28, 42),
+                      disable_conv_head=True)
+    v0 = model._versions()
+    model._packed_versions = v0
+    model.load_state_dict(model.state_dict())
+    assert model._packed_versions is None
+    model._packed_versions = model._versions()
+    model.double()
+    assert model._packed_versions is None
+    assert model._versions() != v0                      # new storages after the dtype change
+    model._packed_versions = model._versions()
+    p = next(model.parameters())
+    with torch.no_grad():
+        p.add_(1.0)
+    assert model._versions() != model._packed_versions  # in-place update bumps the version counter
+    model._packed_versions = model._versions()
+    p.data.add_(1.0)
+    assert model._versions() == model._packed_versions  # .data writes are invisible ...
+    model.invalidate_weights()
+    assert model._packed_versions is None               # ... hence the explicit hook

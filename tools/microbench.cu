@@ -1,0 +1,237 @@
+// Pipe-rate microbenchmarks for sm_100a that the kernel designs in DESIGN.md lean on:
+//   * tcgen05.mma issue interval for the tile shapes of the flash-attention kernel (SS / TS operands,
+//     N = 32..256, K-major / MN-major B, same vs alternating accumulator)
+//   * MUFU ex2 throughput in f32, f16x2 and bf16x2 form, FFMA vs fma.rn.f32x2, FMNMX
+//   * tcgen05.ld / tcgen05.st throughput
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench tools/microbench.cu
+// Run  :  tools/microbench            (prints one line per measurement; cycles are SM clocks)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../endodav_b200/csrc/tc_common.cuh"
+
+using namespace tc;
+
+#define CK(x)                                                                    \
+  do {                                                                           \
+    cudaError_t e_ = (x);                                                        \
+    if (e_ != cudaSuccess) {                                                     \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(1);                                                                   \
+    }                                                                            \
+  } while (0)
+
+// ---- tcgen05.mma -----------------------------------------------------------------------------
+// One CTA: thread 32 issues `groups` x 4 MMAs (K = 16 each; 4 = one 64-wide k-block), commits, waits.
+// TS: A operand from TMEM (as P in the attention kernel).  BMN: B stored MN-major (as V).
+// ALT: alternate between two accumulators (independent chains) instead of one.
+template <int N, bool TS, bool BMN, bool ALT>
+__global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int groups) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;               // 128 x 64 x 2 = 16 KB
+  unsigned char* sB = smem + 16384;       // 256 x 64 x 2 = 32 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) tmem_alloc(slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = *slot;
+  if (threadIdx.x == 32) {
+    constexpr uint32_t idesc = make_idesc<f16>(128, N, BMN ? 1 : 0);
+    const uint64_t adesc = make_smem_desc(smem_u32(sA), 1024, 16, SWZ_128B);
+    const uint64_t bdesc = BMN ? make_smem_desc(smem_u32(sB), 1024, 1024, SWZ_128B) : make_smem_desc(smem_u32(sB), 1024, 16, SWZ_128B);
+    // warm-up
+    for (int k = 0; k < 4; ++k) {
+      if (TS) mma_ts(tm, tm + 448 + k * 8, bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 0);
+      else mma_ss(tm, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 0);
+    }
+    mma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      const uint32_t d = tm + ((ALT && (g & 1)) ? 256 : 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (TS) mma_ts(d, tm + 448 + k * 8, bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 1);
+        else mma_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 1);
+      }
+    }
+    mma_commit(bar);
+    mbar_wait(bar, 1);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    fence_after_sync();
+    tmem_dealloc(tm, 512);
+  }
+}
+
+template <int N, bool TS, bool BMN, bool ALT> void run_mma(const char* what, long long* d_out, int nblocks) {
+  auto kern = mma_bench<N, TS, BMN, ALT>;
+  const int smem = 1024 + 16384 + 32768 + 64;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int groups = 256;
+  kern<<<nblocks, 128, smem>>>(d_out, groups);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(nblocks);
+  CK(cudaMemcpy(h.data(), d_out, nblocks * sizeof(long long), cudaMemcpyDeviceToHost));
+  double s = 0;
+  for (long long v : h) s += (double)v;
+  const double per = s / nblocks / (groups * 4);
+  printf("mma %-34s N=%3d ctas=%3d: %7.1f cycles / MMA (M=128,K=16)  -> %6.0f MAC/cycle/SM\n", what, N, nblocks, per,
+         128.0 * N * 16 / per);
+}
+
+// ---- ALU / MUFU pipes ---------------------------------------------------------------------------
+enum { OP_EX2_F32 = 0, OP_EX2_F16X2 = 1, OP_EX2_BF16X2 = 2, OP_FFMA = 3, OP_FFMA2 = 4, OP_FMNMX = 5, OP_CVT_F16X2 = 6, OP_FADD = 7 };
+
+template <int OP> __global__ void __launch_bounds__(1024) pipe_bench(float* out, long long* cyc, int iters) {
+  constexpr int U = 8;
+  float x[U];
+  uint32_t h[U];
+  unsigned long long p[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    x[j] = -0.001f * (threadIdx.x + j);
+    h[j] = 0xb800b400u + j;                 // two small negative halves
+    p[j] = ((unsigned long long)__float_as_uint(0.999f) << 32) | __float_as_uint(0.998f);
+  }
+  const unsigned long long cst = ((unsigned long long)__float_as_uint(1e-9f) << 32) | __float_as_uint(1e-9f);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (OP == OP_EX2_F32) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[j]));
+      if (OP == OP_EX2_F16X2) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[j]));
+      if (OP == OP_EX2_BF16X2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(h[j]));
+      if (OP == OP_FFMA) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[j]) : "f"(0.999f), "f"(1e-9f));
+      if (OP == OP_FFMA2) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[j]) : "l"(p[(j + 1) % U]), "l"(cst));
+      if (OP == OP_FMNMX) asm volatile("max.f32 %0, %0, %1;" : "+f"(x[j]) : "f"(x[(j + 1) % U]));
+      if (OP == OP_CVT_F16X2) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(x[j]), "f"(x[(j + 1) % U]));
+      if (OP == OP_FADD) asm volatile("add.f32 %0, %0, %1;" : "+f"(x[j]) : "f"(1e-9f));
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < U; ++j) s += x[j] + __uint_as_float(h[j]) + __uint_as_float((uint32_t)p[j]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP> void run_pipe(const char* what, float* d_f, long long* d_out, int warps) {
+  const int iters = 2048;
+  pipe_bench<OP><<<1, warps * 32>>>(d_f, d_out, iters);
+  CK(cudaDeviceSynchronize());
+  long long c;
+  CK(cudaMemcpy(&c, d_out, sizeof c, cudaMemcpyDeviceToHost));
+  const double instr_per_smsp = (double)iters * 8 * warps / 4.0;
+  printf("pipe %-16s warps/SM=%2d: %6.2f cycles per warp-instruction per SMSP  (%5.1f lanes/clk/SM)\n", what, warps,
+         (double)c / instr_per_smsp, 32.0 * 4 * instr_per_smsp / (double)c);
+}
+
+// ---- tcgen05.ld / st ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) tmem_bench(long long* out, float* sink, int iters, int nwarps_active) {
+  __shared__ uint32_t slot;
+  if (threadIdx.x < 32) tmem_alloc(&slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  float acc = 0.f;
+  long long t_ld = 0, t_st = 0;
+  if (warp < nwarps_active) {
+    float v[32];
+    uint32_t r[16];
+    for (int i = 0; i < 16; ++i) r[i] = i;
+    for (int c = 0; c < 512; c += 16) tmem_st16(tm + lane_off + c, r);
+    tmem_st_wait();
+    __syncwarp();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        tmem_ld32(tm + lane_off + (warp >> 2) * 128 + c, v);
+        acc += v[0] + v[31];
+      }
+    }
+    long long t1 = clock64();
+    t_ld = t1 - t0;
+    t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) tmem_st16(tm + lane_off + 256 + (warp >> 2) * 64 + c, r);
+      tmem_st_wait();
+    }
+    t1 = clock64();
+    t_st = t1 - t0;
+  }
+  sink[threadIdx.x] = acc;
+  if (threadIdx.x == 0) {
+    out[0] = t_ld;
+    out[1] = t_st;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    fence_after_sync();
+    tmem_dealloc(tm, 512);
+  }
+}
+
+int main() {
+  long long* d_out;
+  float* d_f;
+  CK(cudaMalloc(&d_out, 4096 * sizeof(long long)));
+  CK(cudaMalloc(&d_f, 1 << 20));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  printf("SMs: %d\n", sms);
+  for (int nb : {1, sms}) {
+    run_mma<32, false, false, false>("SS K-major", d_out, nb);
+    run_mma<64, false, false, false>("SS K-major", d_out, nb);
+    run_mma<128, false, false, false>("SS K-major", d_out, nb);
+    run_mma<192, false, false, false>("SS K-major", d_out, nb);
+    run_mma<256, false, false, false>("SS K-major", d_out, nb);
+    run_mma<128, false, false, true>("SS K-major, alternating D", d_out, nb);
+    run_mma<64, false, true, false>("SS B MN-major", d_out, nb);
+    run_mma<64, true, true, false>("TS (A in TMEM) B MN-major", d_out, nb);
+    run_mma<64, true, true, true>("TS B MN-major, alternating D", d_out, nb);
+    run_mma<128, true, true, false>("TS (A in TMEM) B MN-major", d_out, nb);
+    run_mma<64, true, false, false>("TS (A in TMEM) B K-major", d_out, nb);
+  }
+  for (int w : {4, 8, 16}) {
+    run_pipe<OP_EX2_F32>("ex2.f32", d_f, d_out, w);
+    run_pipe<OP_EX2_F16X2>("ex2.f16x2", d_f, d_out, w);
+    run_pipe<OP_EX2_BF16X2>("ex2.bf16x2", d_f, d_out, w);
+    run_pipe<OP_FFMA>("fma.f32", d_f, d_out, w);
+    run_pipe<OP_FFMA2>("fma.f32x2", d_f, d_out, w);
+    run_pipe<OP_FMNMX>("max.f32", d_f, d_out, w);
+    run_pipe<OP_CVT_F16X2>("cvt.f16x2.f32", d_f, d_out, w);
+    run_pipe<OP_FADD>("add.f32", d_f, d_out, w);
+  }
+  for (int w : {4, 8}) {
+    const int iters = 512;
+    tmem_bench<<<1, 256>>>(d_out, d_f, iters, w);
+    CK(cudaDeviceSynchronize());
+    long long c[2];
+    CK(cudaMemcpy(c, d_out, sizeof c, cudaMemcpyDeviceToHost));
+    printf("tmem warps=%d: ld 128 cols x 32 lanes: %.1f cycles per warp (%.1f B/cycle/SM);  st 64 cols + wait: %.1f cycles per warp (%.1f B/cycle/SM)\n",
+           w, (double)c[0] / iters, (double)w * 128 * 32 * 4 * iters / c[0], (double)c[1] / iters, (double)w * 64 * 32 * 4 * iters / c[1]);
+  }
+  printf("done\n");
+  return 0;
+}
