@@ -6,5 +6,6 @@ Public surface mirrors the reference: ``from endodav_b200 import endodav`` repla
 from .model import endodav, endodac, parameter_layout  # noqa: F401
 from .engine import EndoDAVError  # noqa: F401
 from . import video  # noqa: F401
+from . import metrics  # noqa: F401
 
-__all__ = ["endodav", "endodac", "parameter_layout", "EndoDAVError", "video"]
+__all__ = ["endodav", "endodac", "parameter_layout", "EndoDAVError", "video", "metrics"]

@@ -6,6 +6,7 @@ its source or ANY header of csrc/ or include/ is newer (the headers are shared t
 import os
 import subprocess
 import sys
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -33,7 +34,10 @@ def _newest_header_mtime():
 
 def _compile(nvcc, src, obj):
     cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    started = time.time()
     res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode == 0 and os.path.exists(obj):
+        os.utime(obj, (started, started))   # a source edited WHILE nvcc was running must still look newer than the object
     return src, cmd, res
 
 

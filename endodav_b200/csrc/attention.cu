@@ -7,13 +7,13 @@
 
 namespace edv {
 
-void attention(Launch& L, int dtype, int engine, const void* qkv, void* out, int F, int S, int heads) {
+void attention(Launch& L, int dtype, int engine, const void* qkv, void* out, int F, int S, int heads, long long* timeline) {
   if (!L.ok()) return;
   // QK^T + PV: 4*S*S*64 per (frame, head); q,k,v read once, o written once
   L.note(4.0 * F * heads * (double)S * S * 64, 4.0 * F * S * heads * 64 * dtype_size(dtype));
   if (dtype != EDV_F32 && engine == EDV_ENGINE_TC) {
-    if (dtype == EDV_BF16) tc::launch_attention_tc<bf16>(L, dtype, qkv, out, F, S, heads, &make_tmap);
-    else tc::launch_attention_tc<f16>(L, dtype, qkv, out, F, S, heads, &make_tmap);
+    if (dtype == EDV_BF16) tc::launch_attention_tc<bf16>(L, dtype, qkv, out, F, S, heads, &make_tmap, timeline);
+    else tc::launch_attention_tc<f16>(L, dtype, qkv, out, F, S, heads, &make_tmap, timeline);
     return;
   }
   dim3 grid((S + 127) / 128, heads, F);

@@ -137,21 +137,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       mbar_arrive(&halo_full[it % CH_STAGES]);
     }
   } else if (warp == 8) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<T>(128, BN, 0);
-      const uint32_t wa = smem_u32(wsm);
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t b = it & 1, ph = (it >> 1) & 1;
-        const uint32_t hs = it % CH_STAGES;
-        mbar_wait(&acc_empty[b], ph ^ 1);
-        mbar_wait(&halo_full[hs], (it / CH_STAGES) & 1);
-        fence_after_sync();
-        const uint32_t ha = smem_u32(halo + hs * HALO_BYTES);
-        // descriptors differ only in the 14-bit start-address field: build once, add offsets (>>4)
-        const uint64_t adesc0 = make_smem_desc(ha, CH_HW * 16, CH_PLANE, 0);
-        const uint64_t bdesc0 = make_smem_desc(wa, 128, BN * 16, 0);
-#pragma unroll 1
+    // ===== MMA issuer (warp-uniform loop, elected lane issues: tc_common.cuh elect_one_sync) =====
+    constexpr uint32_t idesc = make_idesc<T>(128, BN, 0);
+    const uint32_t wa = smem_u32(wsm);
+    const uint32_t leader = elect_one_sync();
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t b = it & 1, ph = (it >> 1) & 1;
+      const uint32_t hs = it % CH_STAGES;
+      mbar_wait(&acc_empty[b], ph ^ 1);
+      mbar_wait(&halo_full[hs], (it / CH_STAGES) & 1);
+      fence_after_sync();
+      const uint32_t ha = smem_u32(halo + hs * HALO_BYTES);
+      // descriptors differ only in the 14-bit start-address field: build once, add offsets (>>4)
+      const uint64_t adesc0 = make_smem_desc(ha, CH_HW * 16, CH_PLANE, 0);
+      const uint64_t bdesc0 = make_smem_desc(wa, 128, BN * 16, 0);
+      if (leader) {
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;
           const uint64_t at = adesc0 + (uint64_t)(ky * CH_HW + kx);                 // 16 B per pixel
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         mma_commit(&halo_empty[hs]);
         mma_commit(&acc_full[b]);
       }
+      __syncwarp();
     }
   } else {
     // ===== epilogue warpgroups =====

@@ -14,6 +14,7 @@
 
 #include "ops.cuh"
 #include "stitch.cuh"
+#include "metrics.cuh"
 
 using namespace edv;
 
@@ -60,6 +61,24 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
+// One captured forward: the launch sequence of Fwd::run for one planned shape and one set of external
+// pointers (the kernel arguments -- including the tensor maps, which are __grid_constant__ parameters -- are
+// baked into the graph's kernel nodes, so nothing is encoded or launched from the host when it is replayed).
+struct GraphEntry {
+  const void* frames = nullptr;
+  const void* disp[4] = {nullptr, nullptr, nullptr, nullptr};
+  const void* resized = nullptr;
+  const void* workspace = nullptr;
+  int u8 = 0, out_h = 0, out_w = 0;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  unsigned long long last_use = 0;
+  bool same(const GraphEntry& o) const {
+    return frames == o.frames && disp[0] == o.disp[0] && disp[1] == o.disp[1] && disp[2] == o.disp[2] && disp[3] == o.disp[3] &&
+           resized == o.resized && workspace == o.workspace && u8 == o.u8 && out_h == o.out_h && out_w == o.out_w;
+  }
+};
+
 struct edv_ctx {
   edv_config cfg;
   std::unordered_map<std::string, WeightRef> weights;
@@ -68,6 +87,21 @@ struct edv_ctx {
   int last_launches = 0;
   int debug = 0;
   int Kp = 640;
+  // CUDA-graph replay of the planned forward (EDV_GRAPH=0 disables): up to GRAPH_SLOTS pointer sets per plan
+  static constexpr int GRAPH_SLOTS = 8;
+  int graph_mode = 1;
+  bool plan_warm = false;              // the first forward of a plan runs eagerly (one-time cudaFuncSetAttribute etc.)
+  int graph_misses = 0;                // consecutive captures without a replay: callers whose pointers never repeat run eagerly
+  unsigned long long graph_clock = 0;
+  std::vector<GraphEntry> graphs;
+  void drop_graphs() {
+    for (GraphEntry& g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+    plan_warm = false;
+    graph_misses = 0;
+  }
+  ~edv_ctx() { drop_graphs(); }
   Profiler prof;
   struct Agg {
     double ms = 0, flops = 0, bytes = 0;
@@ -280,7 +314,6 @@ struct Fwd {
     const Plan& p = c->plan;
     const int F_ = c->cfg.features, Fh = F_ / 2;
     void* o1 = buf("head.o1");
-    void* up = buf("head.up");
     conv3(X, p.BT, H, Wd, F_, c0 + ".w", Fh, ep(o1, Fh, wf(c0 + ".b", Fh)));
     const float* hw_ = wf(c4 + ".w", 33);
     if (tc() && head_fused_supported(dt, Fh)) {
@@ -290,6 +323,7 @@ struct Fwd {
       L.tag.clear();
       return;
     }
+    void* up = buf("head.up");
     upsample(L, dt, o1, up, p.BT, H, Wd, OH, OW, Fh);
     if (tc()) {
       Epi e = ep(out, 1, wf(c2 + ".b", 32));
@@ -562,6 +596,7 @@ int edv_create(const edv_config* cfg, edv_ctx** out) {
     return set_err(nullptr, EDV_ERR_NO_DEVICE, "edv_create: device is sm_%d%d, kernels are built for sm_100a only", prop.major, prop.minor);
   edv_ctx* c = new edv_ctx();
   c->cfg = *cfg;
+  if (const char* env = getenv("EDV_GRAPH")) c->graph_mode = atoi(env) != 0;
   *out = c;
   return EDV_OK;
 }
@@ -573,6 +608,8 @@ const char* edv_last_error(const edv_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int edv_set_weight(edv_ctx* ctx, const char* name, const void* dev_ptr, size_t bytes) {
   if (!ctx || !name || !dev_ptr) return set_err(ctx, EDV_ERR_ARG, "edv_set_weight: null argument");
   if (((uintptr_t)dev_ptr & 15) != 0) return set_err(ctx, EDV_ERR_ARG, "edv_set_weight: '%s' must be 16-byte aligned", name);
+  auto it = ctx->weights.find(name);
+  if (it == ctx->weights.end() || it->second.ptr != dev_ptr || it->second.bytes != bytes) ctx->drop_graphs();   // pointers are baked into captured graphs
   ctx->weights[name] = WeightRef{dev_ptr, bytes};
   return EDV_OK;
 }
@@ -581,6 +618,7 @@ int edv_set_debug(edv_ctx* ctx, int on) {
   if (!ctx) return EDV_ERR_ARG;
   ctx->debug = on;
   ctx->plan.valid = false;
+  ctx->drop_graphs();
   return EDV_OK;
 }
 
@@ -635,6 +673,7 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
     off += (bytes + 1023) & ~(size_t)1023;
   };
   const int D = g.dim;
+  const bool simt = (g.dtype == EDV_F32) || g.engine == EDV_ENGINE_SIMT;
   add("A0", (size_t)p.Mp * KPATCH * es);
   add("x", (size_t)p.M * D * 4, 4);
   add("xn", (size_t)p.M * D * es);
@@ -660,7 +699,7 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
   add("L3", px3 * p.Cp[2] * es);
   add("L4p", px3 * p.Cp[3] * es);
   add("L4", px4 * p.Cp[3] * es);
-  add("col", px4 * 9 * p.Cp[3] * es);
+  if (!simt) add("col", px4 * 9 * p.Cp[3] * es);
   if (!g.no_motion) {
     add("L3m", px3 * p.Cp[2] * es);
     add("L4m", px4 * p.Cp[3] * es);
@@ -684,7 +723,6 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
     add("mm.gg", mm4 * es);
     add("mm.hsT", mmC * es);
   }
-  const bool simt = (g.dtype == EDV_F32) || g.engine == EDV_ENGINE_SIMT;
   if (simt && !g.no_motion) add("mm.gg2", mm8 * es);
   add("l1r", px1 * F_ * es); add("l1rr", px1 * F_ * es);
   add("l2r", px2 * F_ * es); add("l2rr", px2 * F_ * es);
@@ -703,7 +741,8 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
   // disparity head scratch: conv at up to 8ph x 8pw, upsample target up to out_h[0] x out_w[0]
   const size_t pxo = (size_t)p.BT * p.out_h[0] * p.out_w[0];
   add("head.o1", px0 * Fh * es);
-  add("head.up", pxo * Fh * es);
+  const bool fused_head = !simt && head_fused_supported(g.dtype, Fh);   // the upsampled map never exists in HBM then
+  if (!fused_head) add("head.up", pxo * Fh * es);
   if (simt) add("head.t32", pxo * 32 * es);
   for (int s = 0; s < 4; ++s) {
     char n[8];
@@ -739,6 +778,7 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
   }
   p.total = off + 1024;
   p.valid = true;
+  ctx->drop_graphs();
   ctx->plan = p;
   *workspace_bytes = p.total;
   return EDV_OK;
@@ -753,9 +793,101 @@ static int forward_common(edv_ctx* ctx, const void* frames, bool u8, float* cons
   if (u8 && (ctx->plan.H != ctx->plan.h || ctx->plan.W != ctx->plan.w))
     return set_err(ctx, EDV_ERR_ARG, "edv_forward_u8: frames must already be at network resolution");
   float* none[4] = {nullptr, nullptr, nullptr, nullptr};
-  Fwd f(ctx, workspace_dev, (cudaStream_t)stream);
-  return f.run(frames, u8, disp_dev ? disp_dev : none, resized_dev, out_h, out_w);
+  float* const* disp = disp_dev ? disp_dev : none;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool graphable = ctx->graph_mode && !ctx->prof.on && !ctx->debug && ctx->plan_warm;
+  if (!graphable) {
+    Fwd f(ctx, workspace_dev, st);
+    const int rc = f.run(frames, u8, disp, resized_dev, out_h, out_w);
+    if (rc == EDV_OK) ctx->plan_warm = true;
+    return rc;
+  }
+  GraphEntry key;
+  key.frames = frames; key.resized = resized_dev; key.workspace = workspace_dev;
+  for (int s_ = 0; s_ < 4; ++s_) key.disp[s_] = disp[s_];
+  key.u8 = u8; key.out_h = resized_dev ? out_h : 0; key.out_w = resized_dev ? out_w : 0;
+  ++ctx->graph_clock;
+  for (GraphEntry& g : ctx->graphs) {
+    if (!g.same(key)) continue;
+    g.last_use = ctx->graph_clock;
+    ctx->graph_misses = 0;
+    ctx->last_launches = g.launches;
+    if (cudaGraphLaunch(g.exec, st) != cudaSuccess) return set_err(ctx, EDV_ERR_CUDA, "edv_forward: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return EDV_OK;
+  }
+  // a caller whose buffers never repeat (fresh tensors on every call with a cold allocator) would pay a capture per
+  // call: after a few consecutive misses run eagerly, and try again later
+  if (ctx->graph_misses >= 2 * edv_ctx::GRAPH_SLOTS) {
+    if (++ctx->graph_misses > 64) ctx->graph_misses = edv_ctx::GRAPH_SLOTS;
+    Fwd f(ctx, workspace_dev, st);
+    return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+  }
+  ++ctx->graph_misses;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    // the caller is capturing this stream itself: just record our launches into its graph
+    cudaGetLastError();
+    Fwd f(ctx, workspace_dev, st);
+    return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+  }
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    Fwd f(ctx, workspace_dev, st);
+    return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+  }
+  int rc;
+  int launches = 0;
+  {
+    Fwd f(ctx, workspace_dev, st);
+    rc = f.run(frames, u8, disp, resized_dev, out_h, out_w);
+    launches = f.L.count;
+  }
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != EDV_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != EDV_OK) return rc;
+    ctx->graph_mode = 0;   // capture is not possible in this process (e.g. a legacy-stream interaction): stay eager
+    Fwd f(ctx, workspace_dev, st);
+    return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || !exec) {
+    cudaGetLastError();
+    ctx->graph_mode = 0;
+    Fwd f(ctx, workspace_dev, st);
+    return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+  }
+  key.exec = exec;
+  key.launches = launches;
+  key.last_use = ctx->graph_clock;
+  if ((int)ctx->graphs.size() >= edv_ctx::GRAPH_SLOTS) {
+    size_t lru = 0;
+    for (size_t i = 1; i < ctx->graphs.size(); ++i)
+      if (ctx->graphs[i].last_use < ctx->graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(ctx->graphs[lru].exec);
+    ctx->graphs[lru] = key;
+  } else {
+    ctx->graphs.push_back(key);
+  }
+  ctx->last_launches = launches;
+  if (cudaGraphLaunch(exec, st) != cudaSuccess) return set_err(ctx, EDV_ERR_CUDA, "edv_forward: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return EDV_OK;
 }
+
+// 1: replay captured CUDA graphs of the planned forward (default), 0: launch every kernel from the host.
+int edv_set_graph_mode(edv_ctx* ctx, int on) {
+  if (!ctx) return EDV_ERR_ARG;
+  ctx->graph_mode = on ? 1 : 0;
+  if (!on) ctx->drop_graphs();
+  return EDV_OK;
+}
+
+// number of captured graphs currently cached for this plan (tests / bench evidence)
+int edv_graph_count(const edv_ctx* ctx) { return ctx ? (int)ctx->graphs.size() : 0; }
 
 int edv_forward(edv_ctx* ctx, const float* frames_dev, float* const disp_dev[4], float* resized_dev, int out_h,
                 int out_w, void* workspace_dev, void* stream) {
@@ -899,6 +1031,17 @@ int edv_op_attention(int dtype, int engine, const void* qkv, void* out, int F, i
   return finish(L);
 }
 
+// edv_op_attention with the in-kernel timeline of the tcgen05 kernel: timeline_dev receives 8 x 64 clock64 stamps
+// (slot meanings in attention_tc.cuh); evidence for DESIGN.md's per-iteration cycle budget, not a product path.
+int edv_op_attention_timeline(int dtype, const void* qkv, void* out, int F, int S, int heads, long long* timeline_dev, void* stream) {
+  if (dtype == EDV_F32 || !timeline_dev) return EDV_ERR_ARG;
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  if (cudaMemsetAsync(timeline_dev, 0, 8 * 64 * sizeof(long long), L.stream) != cudaSuccess) return EDV_ERR_CUDA;
+  attention(L, dtype, EDV_ENGINE_TC, qkv, out, F, S, heads, timeline_dev);
+  return finish(L);
+}
+
 int edv_op_temporal_attention(int dtype, const void* qkv, void* out, int B, int T, int hw, int C, void* stream) {
   Launch L;
   L.stream = (cudaStream_t)stream;
@@ -955,6 +1098,32 @@ int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int
   Launch L;
   L.stream = (cudaStream_t)stream;
   resize_f32(L, X, Y, F, h, w, oh, ow);
+  return finish(L);
+}
+
+int edv_op_disp_to_depth(const float* disp_dev, float* scaled_disp_dev, float* depth_dev, long long n, double min_depth,
+                         double max_depth, void* stream) {
+  if (!disp_dev || !depth_dev || n < 1 || !(min_depth > 0) || !(max_depth > 0)) return EDV_ERR_ARG;
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  const double min_disp = 1.0 / max_depth, max_disp = 1.0 / min_depth;   // Python floats in the reference
+  L.note(0, (double)n * (scaled_disp_dev ? 12 : 8));
+  disp_to_depth_kernel<<<nblk(n, 256), 256, 0, L.stream>>>(disp_dev, scaled_disp_dev, depth_dev, n, (float)min_disp,
+                                                         (float)(max_disp - min_disp));
+  L.check("disp_to_depth");
+  return finish(L);
+}
+
+int edv_op_compute_errors(const float* gt_dev, const float* pred_dev, const uint8_t* mask_dev, int frames, long long hw,
+                          float gt_lo, float gt_hi, float pred_scale, float clamp_lo, float clamp_hi, double* out_dev,
+                          void* stream) {
+  if (!gt_dev || !pred_dev || !out_dev || frames < 1 || hw < 1) return EDV_ERR_ARG;
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  L.note(0, (double)frames * hw * (mask_dev ? 9 : 8));
+  compute_errors_kernel<<<frames, CE_THREADS, 0, L.stream>>>(gt_dev, pred_dev, mask_dev, hw, gt_lo, gt_hi, pred_scale, clamp_lo,
+                                                            clamp_hi, out_dev);
+  L.check("compute_errors");
   return finish(L);
 }
 

@@ -20,8 +20,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
   __shared__ float Ws[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const long long m0 = (long long)blockIdx.y * SG_BM;
-  const int n0 = blockIdx.x * SG_BN;
+  const long long m0 = (long long)blockIdx.x * SG_BM;   // M tiles on grid.x: 32 x 518 x 518 output pixels are 134 k tiles (> 65535)
+  const int n0 = blockIdx.y * SG_BN;
   // loader mapping: 64 rows x 16 k, 4 consecutive k per thread
   const int lr = tid >> 2, lk = (tid & 3) * 4;
   const long long am = m0 + lr;

@@ -375,21 +375,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<T>(GT_BM, BN, 0);
-      uint32_t kc = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t b = it & 1;
-        mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+    // warp-uniform issue loop: all 32 lanes wait on the barriers and build the descriptors, the elected lane
+    // issues tcgen05.mma / tcgen05.commit (see elect_one_sync in tc_common.cuh)
+    constexpr uint32_t idesc = make_idesc<T>(GT_BM, BN, 0);
+    const uint32_t leader = elect_one_sync();
+    uint32_t kc = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1;
+      mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+      fence_after_sync();
+      const uint32_t acc = tmem_base + b * BN;
+      for (int kb = 0; kb < kblocks; ++kb, ++kc) {
+        const int s = kc % stages;
+        mbar_wait(&full_bar[s], (kc / stages) & 1);
         fence_after_sync();
-        const uint32_t acc = tmem_base + b * BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++kc) {
-          const int s = kc % stages;
-          mbar_wait(&full_bar[s], (kc / stages) & 1);
-          fence_after_sync();
-          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc(sa, SBO, 16, SWZ);
-          const uint64_t bdesc = make_smem_desc(sa + A_BYTES, SBO, 16, SWZ);
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa, SBO, 16, SWZ);
+        const uint64_t bdesc = make_smem_desc(sa + A_BYTES, SBO, 16, SWZ);
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
@@ -397,8 +400,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           mma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
         }
-        mma_commit(&tfull_bar[b]);    // accumulator complete
+        __syncwarp();
       }
+      if (leader) mma_commit(&tfull_bar[b]);    // accumulator complete
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // epilogue warpgroups 0..3: accumulator buffer g = wg & 1, column half = wg >> 1;

@@ -127,8 +127,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
+      // warp-uniform issue loop in the leader CTA (elect_one_sync, tc_common.cuh)
       constexpr uint32_t idesc = make_idesc<T>(256, BN, 0);
+      const uint32_t issuer = elect_one_sync();
       uint32_t kc = 0, it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
         const uint32_t b = it & 1;
@@ -142,12 +144,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa, 1024, 16, SWZ_128B);
           const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 1024, 16, SWZ_128B);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            mma_ss_2sm(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          mma_commit_2sm(&empty_bar[s]);
+            for (int k = 0; k < BK / 16; ++k)
+              mma_ss_2sm(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            mma_commit_2sm(&empty_bar[s]);
+          }
+          __syncwarp();
         }
-        mma_commit_2sm(&tfull_bar[b]);
+        if (issuer) mma_commit_2sm(&tfull_bar[b]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -172,33 +172,36 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
       mbar_arrive(&halo_full[b]);
     }
   } else if (warp == 4) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<T>(128, 32, 0);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t b = it & 1, ph = (it >> 1) & 1;
-        const uint32_t hs = it % HF_STAGES;
-        mbar_wait(&acc_empty[b], ph ^ 1);
-        mbar_wait(&halo_full[hs], (it / HF_STAGES) & 1);
-        fence_after_sync();
-        const uint32_t ha = smem_u32(halo + hs * HALO_BYTES);
-        const uint32_t wa = smem_u32(wsm);
-        uint32_t first = 1;
+    // ===== MMA issuer (warp-uniform loop, elected lane issues: tc_common.cuh elect_one_sync) =====
+    constexpr uint32_t idesc = make_idesc<T>(128, 32, 0);
+    const uint32_t leader = elect_one_sync();
+    const uint32_t wa = smem_u32(wsm);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1, ph = (it >> 1) & 1;
+      const uint32_t hs = it % HF_STAGES;
+      mbar_wait(&acc_empty[b], ph ^ 1);
+      mbar_wait(&halo_full[hs], (it / HF_STAGES) & 1);
+      fence_after_sync();
+      const uint32_t ha = smem_u32(halo + hs * HALO_BYTES);
+      const uint64_t adesc0 = make_smem_desc(ha, HF_HW * 16, HF_PLANE, 0);
+      const uint64_t bdesc0 = make_smem_desc(wa, 128, 512, 0);
+      if (leader) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;
 #pragma unroll
           for (int k = 0; k < CIN / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(ha + (2 * k) * HF_PLANE + (ky * HF_HW + kx) * 16, HF_HW * 16, HF_PLANE, 0);
-            const uint64_t bdesc = make_smem_desc(wa + (tap * NCH + 2 * k) * 512, 128, 512, 0);
-            mma_ss(tmem_base + b * 32, adesc, bdesc, idesc, first ? 0u : 1u);
-            first = 0;
+            // start-address field is in 16-byte units: halo pixel = 16 B, chunk plane = HF_PLANE B, weight chunk = 512 B
+            const uint64_t adesc = adesc0 + (uint64_t)((2 * k) * (HF_PLANE / 16) + (ky * HF_HW + kx));
+            const uint64_t bdesc = bdesc0 + (uint64_t)((tap * NCH + 2 * k) * 32);
+            mma_ss(tmem_base + b * 32, adesc, bdesc, idesc, (tap | k) ? 1u : 0u);
           }
         }
         mma_commit(&halo_empty[hs]);
         mma_commit(&acc_full[b]);
       }
+      __syncwarp();
     }
   } else {
     // ===== epilogue =====

@@ -127,7 +127,8 @@ inline void pick_conv_tile(int H, int W, int* th, int* tw) {
 template <typename T> void launch_gemm_tc_lin(Launch& L, int dtype, const GemmArgs& a);
 template <typename T> void launch_gemm_tc_conv(Launch& L, int dtype, const GemmArgs& a);
 // attention.cu: spatial flash attention (tcgen05) / CUDA-core attention, temporal attention
-void attention(Launch& L, int dtype, int engine, const void* qkv, void* out, int F, int S, int heads);
+void attention(Launch& L, int dtype, int engine, const void* qkv, void* out, int F, int S, int heads,
+               long long* timeline = nullptr);
 void temporal_attention(Launch& L, int dtype, const void* qkv, void* out, int B, int Tn, int hw, int C,
                         const float* rope = nullptr);
 // head.cu: fused upsample -> conv3x3 -> ReLU -> 1x1 -> ReLU|sigmoid

@@ -15,6 +15,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- single-thread election ---------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / TMA are issued by ONE thread, but the code around them must stay
+// WARP-UNIFORM: when a whole role is wrapped in `if (lane == 0)`, nvcc cannot prove that the descriptors
+// and TMEM addresses are warp-uniform and brackets every UTCHMMA with an R2UR.BROADCAST / BRA.U.ANY
+// uniformisation loop -- measured with tools/microbench.cu: 60-62 cycles per MMA regardless of N, against
+// 32 cycles (A in TMEM, N = 64) or 40-48 cycles (A in shared memory, N = 32-64) when all 32 lanes run the
+// loop and only the instruction itself is predicated on this flag.  elect.sync with a full mask returns the
+// same lane every time, so the flag is computed once per role (commit must come from the thread that issued
+// the MMAs).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -16,14 +16,15 @@ DTYPES = {"fp32": EDV_F32, "f32": EDV_F32, "float32": EDV_F32, "bf16": EDV_BF16,
           "fp16": EDV_F16, "f16": EDV_F16, "float16": EDV_F16}
 TORCH_DTYPE = {EDV_F32: torch.float32, EDV_BF16: torch.bfloat16, EDV_F16: torch.float16}
 
-ABI_VERSION = 3   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
+ABI_VERSION = 6   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
 
 EXPORTS = [
     "edv_abi_version", "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
-    "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_plan_buffer", "edv_op_linear", "edv_op_conv3x3",
+    "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_plan_buffer", "edv_set_graph_mode", "edv_graph_count", "edv_op_linear", "edv_op_conv3x3",
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
     "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
     "edv_op_disp_head", "edv_op_cubic_resize_u8", "edv_op_stitch_window", "edv_op_stitch_plan",
+    "edv_op_disp_to_depth", "edv_op_compute_errors", "edv_op_attention_timeline",
 ]
 
 
@@ -74,6 +75,8 @@ def load_library():
     lib.edv_debug_tap.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_longlong),
                                   ctypes.POINTER(ci)]
     lib.edv_plan_buffer.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(sz), ctypes.POINTER(sz), ctypes.POINTER(ci)]
+    lib.edv_set_graph_mode.argtypes = [vp, ci]
+    lib.edv_graph_count.argtypes = [vp]
     lib.edv_profile.argtypes = [vp, ci]
     lib.edv_profile_reset.argtypes = [vp]
     lib.edv_profile_collect.argtypes = [vp]
@@ -83,11 +86,15 @@ def load_library():
     lib.edv_op_linear.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.edv_op_conv3x3.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.edv_op_attention.argtypes = [ci, ci, vp, vp, ci, ci, ci, vp]
+    lib.edv_op_attention_timeline.argtypes = [ci, vp, vp, ci, ci, ci, vp, vp]
     lib.edv_op_temporal_attention.argtypes = [ci, vp, vp, ci, ci, ci, ci, vp]
     lib.edv_op_disp_head.argtypes = [ci, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, vp]
     lib.edv_op_cubic_resize_u8.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     lib.edv_op_stitch_window.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, vp, vp]
     lib.edv_op_stitch_plan.argtypes = [ci, ci, vp, ctypes.c_longlong]
+    lib.edv_op_disp_to_depth.argtypes = [vp, vp, vp, ctypes.c_longlong, ctypes.c_double, ctypes.c_double, vp]
+    lib.edv_op_compute_errors.argtypes = [vp, vp, vp, ci, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_float, ctypes.c_float, vp, vp]
     lib.edv_op_layernorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ctypes.c_float, vp]
     lib.edv_op_groupnorm.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, vp]
     lib.edv_op_upsample.argtypes = [ci, vp, vp, ci, ci, ci, ci, ci, ci, vp]
@@ -197,6 +204,13 @@ class Engine:
         _check(rc, self.ctx, "edv_forward")
         return disp, resized
 
+    def set_graph_mode(self, on: bool):
+        """CUDA-graph replay of the planned forward (default on); see include/endodav_b200.h."""
+        _check(self.lib.edv_set_graph_mode(self.ctx, int(on)), self.ctx, "edv_set_graph_mode")
+
+    def graph_count(self):
+        return int(self.lib.edv_graph_count(self.ctx))
+
     def launch_count(self):
         return int(self.lib.edv_launch_count(self.ctx))
 
@@ -276,6 +290,16 @@ def op_attention(qkv, F, S, heads, engine=ENGINE_TC):
     return out
 
 
+def op_attention_timeline(qkv, F, S, heads):
+    """-> (out, int64 [8,64] clock64 stamps of the first 8 CTAs); slot table in csrc/attention_tc.cuh."""
+    lib = load_library()
+    out = torch.empty(F * S, heads * 64, dtype=qkv.dtype, device=qkv.device)
+    tl = torch.zeros(8, 64, dtype=torch.int64, device=qkv.device)
+    _check(lib.edv_op_attention_timeline(_dt(qkv), _ptr(qkv), _ptr(out), F, S, heads, _ptr(tl), _stream()), None,
+           "edv_op_attention_timeline")
+    return out, tl
+
+
 def op_temporal_attention(qkv, B, T, hw, C):
     lib = load_library()
     out = torch.empty(B * T * hw, C, dtype=qkv.dtype, device=qkv.device)
@@ -292,11 +316,14 @@ def op_disp_head(X, Wt, bias, head_w, oh, ow, sig_sign=0.0):
     return out
 
 
-def op_cubic_resize_u8(frames_u8, h, w):
+def op_cubic_resize_u8(frames_u8, h, w, out=None):
     """uint8 [N,H,W,3] (device) -> float32 [N,3,h,w]: the reference's per-frame cv2 cubic resize of frame/255."""
     lib = load_library()
     N, H, W, _ = frames_u8.shape
-    out = torch.empty(N, 3, h, w, dtype=torch.float32, device=frames_u8.device)
+    if out is None:
+        out = torch.empty(N, 3, h, w, dtype=torch.float32, device=frames_u8.device)
+    elif tuple(out.shape) != (N, 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise EndoDAVError("op_cubic_resize_u8: out must be a contiguous float32 [%d,3,%d,%d] tensor" % (N, h, w))
     _check(lib.edv_op_cubic_resize_u8(_ptr(frames_u8), _ptr(out), N, H, W, h, w, _stream()), None, "edv_op_cubic_resize_u8")
     return out
 

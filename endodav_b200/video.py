@@ -272,6 +272,12 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
             pinned = [torch.empty(WB, INFER_LEN, 3, new_h, new_w, dtype=torch.float32, pin_memory=True) for _ in range(2)]
         copied = [None, None]
         calls = [0]
+        # device staging is allocated once and reused (two slots): besides saving allocator traffic this keeps the
+        # external pointers of edv_forward stable, so the captured CUDA graph of the forward is replayed for every
+        # window batch instead of re-launching ~190 kernels from the host
+        dev_u8 = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)] if gpu_pre else None
+        dev_x = [torch.empty(WB * INFER_LEN, 3, new_h, new_w, dtype=torch.float32, device=dev) for _ in range(2)]
+        dev_out = [None, None]
 
         def launch(j, nb=1, out=None):
             """enqueue windows mine[j:j+nb]: H2D of their frames, (cubic resize,) forward, resize back ->
@@ -282,21 +288,27 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                 copied[slot].synchronize()  # the earlier H2D copy out of this buffer has finished
             buf = pinned[slot]
             idx = np.concatenate([window_frame_indices(mine[j + b], n) for b in range(nb)])
+            x = dev_x[slot][: nb * INFER_LEN]
             if gpu_pre:
                 np.take(frames, idx, axis=0, out=buf.numpy()[: nb * INFER_LEN])
-                xu8 = buf[: nb * INFER_LEN].to(dev, non_blocking=True)
+                xu8 = dev_u8[slot][: nb * INFER_LEN]
+                xu8.copy_(buf[: nb * INFER_LEN], non_blocking=True)
             else:
                 flat = buf.view(WB * INFER_LEN, 3, new_h, new_w)
                 for i, src in enumerate(idx):
                     flat[i].copy_(torch.from_numpy(cache.get(int(src))))
-                x = buf[:nb].to(dev, non_blocking=True)
+                x.copy_(flat[: nb * INFER_LEN], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             copied[slot] = ev
             if gpu_pre:
-                x = _engine.op_cubic_resize_u8(xu8, new_h, new_w).view(nb, INFER_LEN, 3, new_h, new_w)
+                _engine.op_cubic_resize_u8(xu8, new_h, new_w, out=x)
+            if out is None:
+                if dev_out[slot] is None:
+                    dev_out[slot] = torch.empty(WB * INFER_LEN, H, W, dtype=torch.float32, device=dev)
+                out = dev_out[slot][: nb * INFER_LEN]
             eng.plan(nb, INFER_LEN, new_h, new_w, ih, iw)
-            return eng.forward(x, resize_to=(H, W), want_pyramid=False, resized_out=out)[1]
+            return eng.forward(x.view(nb, INFER_LEN, 3, new_h, new_w), resize_to=(H, W), want_pyramid=False, resized_out=out)[1]
 
         if world == 1 and gpu_stitch:
             # Single GPU, default: every window is aligned / cross-faded on the device right behind its forward
@@ -349,46 +361,56 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                 if rank == 0:
                     with torch.cuda.stream(side):
                         st = _GpuStitcher(nwin, n, H, W, dev, splan)
-                inflight = []      # (send, bufs, work) of rounds whose gather may still be running
+                # Three rotating sets of gather buffers (round r uses set r % 3): bounded memory however long the video,
+                # and stable pointers, so the forward's captured CUDA graph is replayed.  Set r % 3 is reused by round
+                # r + 3 once (a) this rank has waited for round r's gather (its `send` is free) and (b) on rank 0 the
+                # side stream has stitched round r out of its receive buffers (`consumed` event).
+                POOL = 3
+                sends = [torch.empty(WB, INFER_LEN, H, W, dtype=torch.float32, device=dev) for _ in range(POOL)]
+                recvs = [[torch.empty(WB, INFER_LEN, H, W, dtype=torch.float32, device=dev) for _ in range(world)]
+                         for _ in range(POOL)] if rank == 0 else None
+                works = [None] * POOL
+                consumed = [None] * POOL
 
-                def consume(j0, nb, bufs, work):
+                def consume(r, j0, nb, bufs, work):
                     with torch.cuda.stream(side):
                         work.wait()                                   # side stream waits for this round's gather
                         for s_ in range(nb):
                             for w_ in range(world):
                                 if (j0 + s_) * world + w_ < nwin:
                                     st.push(bufs[w_][s_])
-                        for b_ in bufs:
-                            b_.record_stream(side)          # freed by the caller below: keep the memory until the side stream is done
+                        consumed[r % POOL] = torch.cuda.Event()
+                        consumed[r % POOL].record(side)
 
                 prev = None
-                for j0 in range(0, per, WB):
+                for r, j0 in enumerate(range(0, per, WB)):
                     nb = min(WB, per - j0)
                     have = max(0, min(nb, len(mine) - j0))             # real windows of this rank in the round
-                    send = torch.empty(nb, INFER_LEN, H, W, dtype=torch.float32, device=dev)
+                    if works[r % POOL] is not None:
+                        works[r % POOL].wait()                         # round r-3's gather has read this send buffer
+                    if rank == 0 and consumed[r % POOL] is not None:
+                        torch.cuda.current_stream().wait_event(consumed[r % POOL])
+                    send = sends[r % POOL][:nb]
                     if have:
                         launch(j0, have, send[:have].view(have * INFER_LEN, H, W))
                     if have < nb:
                         send[have:].zero_()
-                    bufs = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+                    bufs = [t[:nb] for t in recvs[r % POOL]] if rank == 0 else None
                     work = dist.gather(send, bufs, dst=0, async_op=True)
-                    inflight.append((send, bufs, work))
+                    works[r % POOL] = work
                     if rank == 0:
                         if prev is not None:
                             consume(*prev)
-                        prev = (j0, nb, bufs, work)
-                    # rounds older than the previous one are finished with: release their buffers (a whole video's
-                    # worth of gather buffers would otherwise stay allocated on rank 0 until the end)
-                    while len(inflight) > 2:
-                        inflight.pop(0)[2].wait()
+                        prev = (r, j0, nb, bufs, work)
                 if rank == 0:
                     consume(*prev)
                     with torch.cuda.stream(side):
                         result = st.finish()
                     torch.cuda.current_stream().synchronize()
                     return result
-                for _, _, work in inflight:
-                    work.wait()
+                for work in works:
+                    if work is not None:
+                        work.wait()
                 torch.cuda.current_stream().synchronize()
                 return None
         # ENDODAV_GATHER=single: every window's disparity is written straight into this rank's (padded) slice of

@@ -30,7 +30,7 @@ typedef struct edv_ctx edv_ctx;
 /* Bumped whenever an entry point's argument list or a struct layout changes.  The ctypes host
  * (endodav_b200/engine.py) mirrors the signatures by hand, so it refuses a library whose
  * edv_abi_version() differs from its own constant instead of calling it with a stale layout. */
-#define EDV_ABI_VERSION 3
+#define EDV_ABI_VERSION 6
 int edv_abi_version(void);
 
 enum edv_status {
@@ -105,6 +105,15 @@ int edv_forward_u8(edv_ctx* ctx, const uint8_t* frames_dev, float* const disp_de
 
 int edv_output_shape(const edv_ctx* ctx, int scale, int* h, int* w);
 
+/* CUDA-graph replay.  After the first (eager) forward of a plan, edv_forward captures its launch sequence into a
+ * cudaGraphExec keyed by the external pointers of the call (frames, disp[], resized, workspace) and replays it on
+ * later calls with the same pointers: no tensor-map encoding and one host launch instead of ~190 -- what the
+ * reference's production resolution (224x280, evaluate_depth_video.py:86) needs, where the forward is launch bound.
+ * Up to 8 pointer sets are cached per plan; edv_plan, edv_set_weight (new pointer) and edv_set_debug drop them;
+ * profiling (edv_profile) and debug taps run eagerly.  Default on (environment EDV_GRAPH=0 turns it off). */
+int edv_set_graph_mode(edv_ctx* ctx, int on);
+int edv_graph_count(const edv_ctx* ctx);
+
 /* Number of kernels the last edv_forward launched (bench.py's gpu_launches). */
 int edv_launch_count(const edv_ctx* ctx);
 
@@ -148,6 +157,12 @@ int edv_op_conv3x3(int dtype, int engine, const void* X, const void* Wt, const f
 /* Spatial multi-head attention over token-major qkv [F*S, 3*heads*64] (q pre-scaled) ->
  * out [F*S, heads*64].  Replaces: Attention.forward's softmax(qk^T)v (attention.py:60-66). */
 int edv_op_attention(int dtype, int engine, const void* qkv, void* out, int F, int S, int heads, void* stream);
+
+/* edv_op_attention (tcgen05 kernel, 16-bit dtypes) that also records the kernel's own timeline: timeline_dev gets
+ * 8 CTAs x 64 clock64 stamps (entry, setup, per-iteration softmax / MMA-issue times; slot table in
+ * csrc/attention_tc.cuh).  Diagnostic evidence for the cycle budget in DESIGN.md. */
+int edv_op_attention_timeline(int dtype, const void* qkv, void* out, int F, int S, int heads, long long* timeline_dev,
+                              void* stream);
 
 /* Temporal attention over the frame axis: qkv [B*T*hw, 3C] (q pre-scaled by hd^-0.5) ->
  * out [B*T*hw, C]; 8 heads; one softmax per (clip, position, head) over T<=32 frames.
@@ -200,6 +215,23 @@ int edv_op_resize_f32(const float* X, float* Y, int F, int h, int w, int oh, int
 long long edv_op_stitch_plan(int H, int W, int32_t* plan_host, long long cap);
 int edv_op_stitch_window(const float* win_dev, int k, int H, int W, float* out_dev, const int32_t* plan_dev, int n_leaves,
                          float* scratch_dev, float* scale_shift_dev, void* stream);
+
+/* Depth conversion of the evaluate scripts on the GPU: scaled_disp = 1/max_depth + (1/min_depth - 1/max_depth) * disp,
+ * depth = 1 / scaled_disp over n float32 elements (scaled_disp_dev may be NULL).  float32 arithmetic op for op, so the
+ * result is bit-identical to the numpy expression.  Replaces disp_to_depth (utils/layers.py:11-20) as called at
+ * evaluate_depth_video.py:170. */
+int edv_op_disp_to_depth(const float* disp_dev, float* scaled_disp_dev, float* depth_dev, long long n, double min_depth,
+                         double max_depth, void* stream);
+
+/* Per-frame depth metrics: out_dev[f][0..7] = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, valid-pixel count (float64)
+ * for frames f of gt_dev / pred_dev [frames][hw] float32.  Valid pixels: mask_dev (uint8 [frames][hw]) when given, else
+ * gt in (gt_lo, gt_hi); pred is multiplied by pred_scale and clamped to [clamp_lo, clamp_hi] first (clamp_lo > clamp_hi
+ * skips the clamp).  One block per frame, fixed summation order (bit-reproducible); a frame without valid pixels gives
+ * NaNs like numpy.  Replaces compute_errors (utils/utils.py:112-133) and the per-frame masking / scaling / clamping
+ * loop around it (evaluate_depth_video.py:197-204). */
+int edv_op_compute_errors(const float* gt_dev, const float* pred_dev, const uint8_t* mask_dev, int frames, long long hw,
+                          float gt_lo, float gt_hi, float pred_scale, float clamp_lo, float clamp_hi, double* out_dev,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -163,6 +163,38 @@ def make_fullsize(manifest):
         del model, out
 
 
+def make_metrics():
+    """disp_to_depth / compute_errors of the UNMODIFIED reference on the seeded case of oracle/metrics_oracle.py."""
+    import importlib.util
+    import warnings
+
+    from oracle import metrics_oracle as mo
+
+    def load(path, name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref_import.REFERENCE_ROOT, path))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    layers = load("utils/layers.py", "ref_utils_layers")
+    utils = load("utils/utils.py", "ref_utils_utils")
+    disp, gt = mo.make_case()
+    scaled, depth = layers.disp_to_depth(disp, 0.1, 150.0)
+    errs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for g, p in zip(gt, depth):
+            p = p.copy()
+            valid = np.logical_and(g > 1e-3, g < 150)
+            p *= 1.0
+            p[p < 1e-3] = 1e-3
+            p[p > 150] = 150
+            errs.append(utils.compute_errors(g, p, valid))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "metrics.npz"), scaled=scaled.astype(np.float32), depth=depth.astype(np.float32),
+                        errors=np.array(errs, dtype=np.float64))
+    print("metrics", scaled.dtype, depth.dtype, np.array(errs)[:2])
+
+
 def stub_forward(x):
     """Deterministic stand-in network used for the bit-exact index/stitch fixtures: per-frame
     disparity = channel mean + 0.1*frame-mean, so every slot's source frame is identifiable."""
@@ -176,6 +208,9 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref_mod = ref_import.import_reference()
     manifest = {}
+    if "--metrics-only" in sys.argv:   # evaluation helpers (utils/layers.py, utils/utils.py) -> tests/golden/metrics.npz
+        make_metrics()
+        return
     if "--fullsize-only" in sys.argv:  # add the full-size fixtures without regenerating the others
         with open(os.path.join(GOLDEN_DIR, "manifest.json")) as f:
             manifest = json.load(f)
@@ -248,6 +283,7 @@ def main():
 
     make_endodac(manifest)
     make_fullsize(manifest)
+    make_metrics()
 
     with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)

@@ -77,6 +77,89 @@ __global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int groups) 
   }
 }
 
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+
+// Same measurement with a WARP-UNIFORM issue loop: every lane of warp 1 runs the loop and only the tcgen05
+// instructions are predicated on elect.sync, so the descriptors live in uniform registers (no per-MMA
+// R2UR.BROADCAST / BRA.U.ANY uniformisation loop as in the single-lane version above).
+template <int N, bool TS, bool BMN, bool ALT>
+__global__ void __launch_bounds__(128, 1) mma_bench_uniform(long long* out, int groups) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) tmem_alloc(slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = *slot;
+  if ((threadIdx.x >> 5) == 1) {
+    constexpr uint32_t idesc = make_idesc<f16>(128, N, BMN ? 1 : 0);
+    const uint64_t adesc = make_smem_desc(smem_u32(sA), 1024, 16, SWZ_128B);
+    const uint64_t bdesc = BMN ? make_smem_desc(smem_u32(sB), 1024, 1024, SWZ_128B) : make_smem_desc(smem_u32(sB), 1024, 16, SWZ_128B);
+    const uint32_t leader = elect_one();
+    if (leader) {
+      for (int k = 0; k < 4; ++k) {
+        if (TS) mma_ts(tm, tm + 448 + k * 8, bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 0);
+        else mma_ss(tm, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 0);
+      }
+      mma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      const uint32_t d = tm + ((ALT && (g & 1)) ? 256 : 0);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (TS) mma_ts(d, tm + 448 + k * 8, bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 1);
+          else mma_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(BMN ? 128 * k : 2 * k), idesc, 1);
+        }
+      }
+      __syncwarp();
+    }
+    if (leader) mma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 1);
+    const long long t1 = clock64();
+    if (leader) out[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    fence_after_sync();
+    tmem_dealloc(tm, 512);
+  }
+}
+
+template <int N, bool TS, bool BMN, bool ALT> void run_mma_u(const char* what, long long* d_out, int nblocks) {
+  auto kern = mma_bench_uniform<N, TS, BMN, ALT>;
+  const int smem = 1024 + 16384 + 32768 + 64;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int groups = 256;
+  kern<<<nblocks, 128, smem>>>(d_out, groups);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(nblocks);
+  CK(cudaMemcpy(h.data(), d_out, nblocks * sizeof(long long), cudaMemcpyDeviceToHost));
+  double s = 0;
+  for (long long v : h) s += (double)v;
+  const double per = s / nblocks / (groups * 4);
+  printf("mma-uniform %-26s N=%3d ctas=%3d: %7.1f cycles / MMA (M=128,K=16)  -> %6.0f MAC/cycle/SM\n", what, N, nblocks, per,
+         128.0 * N * 16 / per);
+}
+
 template <int N, bool TS, bool BMN, bool ALT> void run_mma(const char* what, long long* d_out, int nblocks) {
   auto kern = mma_bench<N, TS, BMN, ALT>;
   const int smem = 1024 + 16384 + 32768 + 64;
@@ -212,6 +295,15 @@ int main() {
     run_mma<64, true, true, true>("TS B MN-major, alternating D", d_out, nb);
     run_mma<128, true, true, false>("TS (A in TMEM) B MN-major", d_out, nb);
     run_mma<64, true, false, false>("TS (A in TMEM) B K-major", d_out, nb);
+  }
+  for (int nb : {1, sms}) {
+    run_mma_u<32, false, false, false>("SS K-major", d_out, nb);
+    run_mma_u<64, false, false, false>("SS K-major", d_out, nb);
+    run_mma_u<128, false, false, false>("SS K-major", d_out, nb);
+    run_mma_u<256, false, false, false>("SS K-major", d_out, nb);
+    run_mma_u<64, true, true, false>("TS B MN-major", d_out, nb);
+    run_mma_u<64, true, true, true>("TS B MN-major, alt D", d_out, nb);
+    run_mma_u<32, false, false, true>("SS K-major, alt D", d_out, nb);
   }
   for (int w : {4, 8, 16}) {
     run_pipe<OP_EX2_F32>("ex2.f32", d_f, d_out, w);
