@@ -123,6 +123,61 @@ __device__ __forceinline__ float gelu_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x * x * (-0.5f * 1.4426950408889634f)));
   return fmaf(-0.5f * ax * p, ex, fmaxf(x, 0.f));
 }
+#define GELU_ZA 9.182736455e-02f
+#define GELU_Q0 3.027377123e-01f
+#define GELU_Q1 -1.496531036e-01f
+#define GELU_Q2 1.075239210e-01f
+#define GELU_Q3 -8.094775278e-02f
+#define GELU_Q4 5.954273902e-02f
+#define GELU_Q5 -4.183582460e-02f
+#define GELU_Q6 2.565362346e-02f
+#define GELU_Q7 -1.271499527e-02f
+#define GELU_Q8 8.149412674e-03f
+#define GELU_Q9 -6.645919508e-03f
+#define GELU_Q10 2.464738470e-03f
+// GELU(erf) for a PAIR without MUFU, in packed fp32x2 arithmetic (FFMA2 / FMUL2; sm_100): erf(x / sqrt2) = xc * Q(xc^2)
+// with xc = clamp(x, +-4.6669) (erf(3.3) = 1 - 3e-6) and Q a degree-10 minimax polynomial evaluated in
+// z = xc^2 * GELU_ZA - 1 in [-1, 1] (the power basis in xc^2 itself loses 5 digits in float32); max |erf error| 3e-6
+// in float32 arithmetic, far below the 16-bit output rounding.  ~9 issue slots per value instead of ~14 + 2 MUFU: the fc1 epilogue is
+// issue / MUFU bound, not math bound (tools/gemm_timeline.py).
+__device__ __forceinline__ void gelu_poly2(float& y0, float& y1, float x0, float x1) {
+  // symmetric clamp in ONE instruction per value: min(|x|, c) with the sign of x (min.xorsign.abs, c > 0)
+  float c0, c1;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(c0) : "f"(x0), "f"(4.66690475f));
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(c1) : "f"(x1), "f"(4.66690475f));
+  unsigned long long xc, xx, t, q, k, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xc) : "f"(c0), "f"(c1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x0), "f"(x1));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(xc));
+  {
+    unsigned long long za, m1;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(za) : "f"(GELU_ZA));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(m1) : "f"(-1.0f));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(t), "l"(za), "l"(m1));
+  }
+  // Q' = Q / 2: Phi(x) = 0.5 + xc * Q'(z)
+#define EDV_GELU_K(v) asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "f"(0.5f * (v)))
+  EDV_GELU_K(GELU_Q10);
+  q = k;
+#define EDV_GELU_STEP(v) EDV_GELU_K(v); asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(q), "l"(t), "l"(k))
+  EDV_GELU_STEP(GELU_Q9);
+  EDV_GELU_STEP(GELU_Q8);
+  EDV_GELU_STEP(GELU_Q7);
+  EDV_GELU_STEP(GELU_Q6);
+  EDV_GELU_STEP(GELU_Q5);
+  EDV_GELU_STEP(GELU_Q4);
+  EDV_GELU_STEP(GELU_Q3);
+  EDV_GELU_STEP(GELU_Q2);
+  EDV_GELU_STEP(GELU_Q1);
+  EDV_GELU_STEP(GELU_Q0);
+#undef EDV_GELU_STEP
+  asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "f"(0.5f));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q) : "l"(q), "l"(xc), "l"(k));   // Phi(x) = 0.5 (1 + erf(x / sqrt2))
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(q), "l"(xx));               // x Phi(x)
+#undef EDV_GELU_K
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(r));
+}
+
 template <typename T> __device__ __forceinline__ float gelu_act(float x) {
   if constexpr (sizeof(T) == 4) return gelu_erf(x);
   else return gelu_fast(x);
@@ -163,6 +218,8 @@ struct Epi {
   float head_b;
   float sig_sign;  // ACT_SIGMOID: sigmoid(sig_sign * x)
   int kind;        // tcgen05 epilogue specialisation (gemm_tc.cuh EF_* mask) or -1: set by the launcher
+  long long* tim;  // optional in-kernel timeline of gemm_tc_kernel (edv_op_linear_timeline), else null
+  int dbg;         // timeline experiments only (EDV_GEMM_DBG): 1 skip the epilogue work, 2 skip the A loads (results are garbage)
 };
 
 // maps GEMM row m -> output row for the column-independent mappings
@@ -238,5 +295,6 @@ __device__ __forceinline__ void epi_apply(const Epi& e, long long m, long long o
 
 // compile-time epilogue kinds of the tcgen05 GEMM (gemm_tc.cuh); Epi::kind holds one of these masks or -1
 namespace tc {
-enum { EF_BIAS = 1, EF_GELU = 2, EF_RELU = 4, EF_RES1_F32 = 8, EF_RES1_T = 16, EF_RES2_T = 32, EF_OUT_F32 = 64, EF_OUT_RELU = 128, EF_ROWBIAS = 256 };
+enum { EF_BIAS = 1, EF_GELU = 2, EF_RELU = 4, EF_RES1_F32 = 8, EF_RES1_T = 16, EF_RES2_T = 32, EF_OUT_F32 = 64, EF_OUT_RELU = 128, EF_ROWBIAS = 256,
+       EF_TMA_OUT = 512 /* 16-bit output written through shared memory + TMA store (gt_epilogue_tma) */ };
 }

@@ -1011,6 +1011,24 @@ int edv_op_linear(int dtype, int engine, const void* A, const void* W, const flo
   return finish(L);
 }
 
+// edv_op_linear on the tcgen05 kernel with its in-kernel timeline: timeline_dev receives 4 x 256 clock64 stamps (slot
+// table in gemm_tc.cuh).  Diagnostic evidence (which role waits on which), not a product path.
+int edv_op_linear_timeline(int dtype, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act,
+                           long long* timeline_dev, void* stream) {
+  if (dtype == EDV_F32 || !timeline_dev) return EDV_ERR_ARG;
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  if (cudaMemsetAsync(timeline_dev, 0, 4 * 256 * sizeof(long long), L.stream) != cudaSuccess) return EDV_ERR_CUDA;
+  GemmArgs a;
+  a.A = A; a.W = W; a.M = M; a.N = N; a.K = K; a.lda = K;
+  a.e = epi_zero();
+  a.e.out = C; a.e.ldo = N; a.e.bias = bias; a.e.act = act;
+  a.e.tim = timeline_dev;
+  if (const char* env = getenv("EDV_GEMM_DBG")) a.e.dbg = atoi(env);
+  gemm(L, dtype, EDV_ENGINE_TC, a);
+  return finish(L);
+}
+
 int edv_op_conv3x3(int dtype, int engine, const void* X, const void* Wt, const float* bias, void* Y, int F, int H,
                    int W, int Cin, int Cout, int relu_out, void* stream) {
   Launch L;

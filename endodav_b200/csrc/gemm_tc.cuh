@@ -36,6 +36,7 @@ struct ConvTile {
 };
 
 constexpr int GT_BM = 128;
+constexpr int GT_PF_KB = 8;   // L2 prefetch distance of the A operand in k-blocks (tc_common.cuh tma_prefetch_2d)
 constexpr int GT_THREADS = 640;
 
 template <int BN, int BK> constexpr int gt_stage_bytes() { return (GT_BM + BN) * BK * 2; }
@@ -295,9 +296,127 @@ __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool va
   }
 }
 
+// ---- TMA-store epilogue (EF_TMA_OUT): 16-bit row-major outputs without residual --------------------------------
+// The row-segment epilogue above costs ~6 000 cycles per 128 x 192 tile even with trivial math (in-kernel timeline,
+// tools/gemm_timeline.py: transposition through shared memory, row-index shuffles, 4-row store instructions), which
+// made qkv / fc1 epilogue-bound at 2 x their mainloop.  Here the accumulator stays in the row-owner domain:
+// thread = row, 32 columns per step: tcgen05.ld -> bias / GELU / ReLU -> pack to 16 bit -> four 16-byte shared-memory
+// stores at 64B-swizzled chunk positions (conflict-free) -> one elected thread issues a TMA store of the
+// 128 x 32 sub-tile (coalescing, M-tail clipping and address arithmetic are the TMA unit's job).  Two 8 KB staging
+// buffers per epilogue warpgroup; cp.async.bulk.wait_group.read gates their reuse.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void wg_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ void add2_f32(float& d0, float& d1, float a0, float a1) {   // packed FADD2
+  unsigned long long ra, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rd) : "f"(d0), "f"(d1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rd) : "l"(ra));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+
+constexpr int GT_OUT_SUB_BYTES = GT_BM * 16 * 2;   // staging of one 128-row x 16-column 16-bit sub-tile (32-byte rows, SWIZZLE_32B)
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait_all() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// All FOUR epilogue warpgroups drain every tile, warpgroup wg columns [wg * BN/4, +BN/4) in 16-column steps
+// (the next tcgen05.ld is in flight while the current step is computed), so the epilogue of tile i takes a quarter
+// of a warpgroup-per-half schedule and runs under the mainloop of tile i+1 (other accumulator buffer).
+// trow: TMEM address of this thread's row at the warpgroup's first column; stg_wg: (BN/64) x 4 KB of staging.
+template <typename T, int BN, int F>
+__device__ __forceinline__ void gt_epilogue_tma(const CUtensorMap* tmC, uint32_t trow, int row0, int col0, int r, int wg,
+                                                unsigned char* stg_wg, const float* bias_s, bool issuer, uint64_t* tempty,
+                                                long long* stamps) {
+  constexpr int CW = BN / 4;
+  constexpr int NSUB = CW / 16;
+  static_assert(CW % 16 == 0 && NSUB >= 1, "TMA-store epilogue needs BN to be a multiple of 64");
+  uint32_t raw[2][16];
+  tmem_ld16_nowait(trow, raw[0]);
+  if ((r >> 5) == 0) {
+    if (elect_one_sync()) tma_store_wait_read<0>();           // the previous tile's stores have read the staging buffers
+    __syncwarp();
+  }
+  if (stamps) stamps[0] = clock64();
+  const int sw = (r >> 2) & 1;                                // SWIZZLE_32B: 16-byte chunk index ^= address bit 7
+#pragma unroll
+  for (int s = 0; s < NSUB; ++s) {
+    tmem_ld_wait_all();
+    if (s + 1 < NSUB) tmem_ld16_nowait(trow + 16 * (s + 1), raw[(s + 1) & 1]);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[s & 1][i]);
+    if (F & EF_BIAS) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + 16 * s + 4 * i);   // warp-wide broadcast
+        add2_f32(v[4 * i], v[4 * i + 1], b.x, b.y);
+        add2_f32(v[4 * i + 2], v[4 * i + 3], b.z, b.w);
+      }
+    }
+    if (F & EF_GELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gelu_poly2(v[2 * i], v[2 * i + 1], v[2 * i], v[2 * i + 1]);
+    }
+    if (F & EF_RELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    uint4 p[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      p[i].x = pack2(from_f<T>(v[8 * i + 0]), from_f<T>(v[8 * i + 1]));
+      p[i].y = pack2(from_f<T>(v[8 * i + 2]), from_f<T>(v[8 * i + 3]));
+      p[i].z = pack2(from_f<T>(v[8 * i + 4]), from_f<T>(v[8 * i + 5]));
+      p[i].w = pack2(from_f<T>(v[8 * i + 6]), from_f<T>(v[8 * i + 7]));
+    }
+    if (s == 0) {
+      if (stamps) stamps[1] = clock64();
+      wg_bar_sync(1 + wg);                                    // staging free (the issuer has passed its wait above)
+      if (stamps) stamps[2] = clock64();
+    }
+    unsigned char* row = stg_wg + s * GT_OUT_SUB_BYTES + r * 32;
+    *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = p[0];
+    *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = p[1];
+    if (s + 1 == NSUB) {
+      // every tcgen05.ld of this thread has completed: hand the accumulator back before the store bookkeeping
+      fence_before_sync();
+      mbar_arrive(tempty);
+    }
+  }
+  if (stamps) stamps[3] = clock64();
+  fence_proxy_async();
+  if (stamps) stamps[4] = clock64();
+  wg_bar_sync(1 + wg);
+  if (stamps) stamps[5] = clock64();
+  if ((r >> 5) == 0) {
+    // warp-uniform branch (warp 0 of the warpgroup), elected lane issues: no uniformisation loops around UTMASTG
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s) tma_store_2d(tmC, stg_wg + s * GT_OUT_SUB_BYTES, col0 + 16 * s, row0);
+      tma_store_commit();
+    }
+    __syncwarp();
+  }
+}
+
 template <typename T, int BN, int BK, bool CONV>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB, Epi e, int M,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmC, Epi e, int M,
                                                                 int N, int K, int stages, ConvTile ct, int n_tiles,
                                                                 int total_tiles) {
   constexpr uint32_t ROW_BYTES = BK * 2;                    // 128 (BK=64) or 64 (BK=32)
@@ -311,27 +430,35 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  // ring stages (multiples of 1 KB) | epilogue staging 64 KB (1 KB aligned: TMA-store source) | bias slices | barriers
+  uint32_t* stg_base = reinterpret_cast<uint32_t*>(smem + (size_t)stages * STAGE_BYTES);   // 16 warps x GT_STG_WORDS
+  float* bias_base = reinterpret_cast<float*>(stg_base + 16 * GT_STG_WORDS);               // 16 warps x 128 floats
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_base + 16 * 128);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;   // 2: accumulator buffer b complete
   uint64_t* tempty_bar = tfull_bar + 2;       // 2: accumulator buffer b drained by its epilogue warpgroup
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint32_t* stg_base = tmem_slot + 4;          // 16 warps x GT_STG_WORDS
-  float* bias_base = reinterpret_cast<float*>(stg_base + 16 * GT_STG_WORDS);   // 16 warps x 128 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = K / BK;
+  // optional timeline (first 4 CTAs, 256 slots each): [0] entry, [1] setup done; per tile i < 20:
+  // [8+4i] MMA: accumulator free (tempty wait done), [9+4i] MMA: last k-block issued, [10+4i] epilogue wg0/wg1: accumulator
+  // complete (tfull wait done), [11+4i] epilogue wg0/wg1: tile stored; [100+i] producer: last load of tile i issued;
+  // [130+kb] MMA: k-block kb of tile 4 ready (full_bar wait done)
+  long long* tm_ = (e.tim && blockIdx.x < 4) ? e.tim + blockIdx.x * 256 : nullptr;
+  if (tm_ && threadIdx.x == 0) tm_[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (e.kind >= 0 && (e.kind & EF_TMA_OUT)) tma_prefetch_desc(&tmC);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 256);
+      mbar_init(&tempty_bar[b], (!CONV && e.kind >= 0 && (e.kind & EF_TMA_OUT)) ? 512 : 256);   // TMA-store mode: all four warpgroups drain every tile
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -341,12 +468,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (tm_ && threadIdx.x == 0) tm_[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
       const int cblocks = CONV ? ct.C / BK : 1;
       uint32_t kc = 0;  // k-blocks issued so far (ring position)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int tile_n = tile % n_tiles, tile_m = tile / n_tiles;
         int cf = 0, y0 = 0, x0 = 0;
         if (CONV) {
@@ -368,10 +497,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
             const int ky = tap / 3, kx = tap - ky * 3;
             tma_load_4d(sa, &tmA, &full_bar[s], c0, x0 + kx - 1, y0 + ky - 1, cf);
           } else {
+            // L2 prefetch of the A k-block GT_PF_KB steps ahead (same tile, or the head of this CTA's next tile)
+            {
+              int pk = kb + GT_PF_KB, pt = tile;
+              if (pk >= kblocks) { pk -= kblocks; pt += gridDim.x; }
+              if (pk < kblocks && pt < total_tiles) tma_prefetch_2d(&tmA, pk * BK, (pt / n_tiles) * GT_BM);
+            }
             tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, tile_m * GT_BM);
           }
           tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, tile_n * BN);
         }
+        if (tm_ && ti < 20) tm_[100 + ti] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -384,11 +520,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t b = it & 1;
       mbar_wait(&tempty_bar[b], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
       fence_after_sync();
+      if (tm_ && leader && it < 20) tm_[8 + 4 * it] = clock64();
       const uint32_t acc = tmem_base + b * BN;
       for (int kb = 0; kb < kblocks; ++kb, ++kc) {
         const int s = kc % stages;
+        if (tm_ && leader && it == 4 && kb < 30) tm_[200 + kb] = clock64();   // [200+kb]: before the wait for k-block kb
         mbar_wait(&full_bar[s], (kc / stages) & 1);
         fence_after_sync();
+        if (tm_ && leader && it == 4 && kb < 30) tm_[130 + kb] = clock64();
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t adesc = make_smem_desc(sa, SBO, 16, SWZ);
         const uint64_t bdesc = make_smem_desc(sa + A_BYTES, SBO, 16, SWZ);
@@ -403,6 +542,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         __syncwarp();
       }
       if (leader) mma_commit(&tfull_bar[b]);    // accumulator complete
+      if (tm_ && leader && it < 20) tm_[9 + 4 * it] = clock64();
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -414,6 +554,46 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row inside the tile
     uint32_t it = 0;
+    const bool tma_out = !CONV && e.kind >= 0 && (e.kind & EF_TMA_OUT);
+    if constexpr (!CONV && BN % 64 == 0) {
+      if (tma_out) {
+        // ---- TMA-store mode: warpgroup wg drains columns [wg * BN/4, +BN/4) of EVERY tile ----
+        constexpr int CW = BN / 4;
+        unsigned char* stg_wg = reinterpret_cast<unsigned char*>(stg_base) + wg * ((CW / 16) * GT_OUT_SUB_BYTES);
+        const bool issuer = (q == 0 && lane == 0);
+        float* bias_s = bias_base + (warp - 4) * 128;
+        const int kind = e.kind & ~EF_TMA_OUT;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          const uint32_t b = it & 1;
+          const int tile_n = tile % n_tiles, tile_m = tile / n_tiles;
+          if (kind & EF_BIAS) {
+            __syncwarp();
+            if (lane < CW) bias_s[lane] = __ldg(e.bias + tile_n * BN + wg * CW + lane);
+            if (CW > 32 && lane + 32 < CW) bias_s[lane + 32] = __ldg(e.bias + tile_n * BN + wg * CW + lane + 32);
+            __syncwarp();
+          }
+          mbar_wait(&tfull_bar[b], (it >> 1) & 1);
+          fence_after_sync();
+          const bool stamp = tm_ && wg == 0 && q == 0 && lane == 0 && it < 20;
+          if (stamp) tm_[10 + 4 * it] = clock64();
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + wg * CW;
+          const int row0 = tile_m * GT_BM, col0 = tile_n * BN + wg * CW;
+          long long* st = (stamp && it == 5) ? tm_ + 170 : nullptr;   // [170..175]: phases of tile 5 (see gt_epilogue_tma)
+          switch (kind) {
+            case EF_BIAS: gt_epilogue_tma<T, BN, EF_BIAS>(&tmC, trow, row0, col0, r, wg, stg_wg, bias_s, issuer, &tempty_bar[b], st); break;
+            case EF_BIAS | EF_GELU: gt_epilogue_tma<T, BN, EF_BIAS | EF_GELU>(&tmC, trow, row0, col0, r, wg, stg_wg, bias_s, issuer, &tempty_bar[b], st); break;
+            case EF_BIAS | EF_RELU: gt_epilogue_tma<T, BN, EF_BIAS | EF_RELU>(&tmC, trow, row0, col0, r, wg, stg_wg, bias_s, issuer, &tempty_bar[b], st); break;
+            default: gt_epilogue_tma<T, BN, 0>(&tmC, trow, row0, col0, r, wg, stg_wg, bias_s, issuer, &tempty_bar[b], st); break;
+          }
+          if (stamp) tm_[11 + 4 * it] = clock64();
+        }
+        if (q == 0) {
+          if (elect_one_sync()) tma_store_wait_all();   // shared memory stays valid until the last store has read it
+          __syncwarp();
+        }
+      }
+    }
+    if (!tma_out) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != g) continue;
       const int tile_n = tile % n_tiles, tile_m = tile / n_tiles;
@@ -447,10 +627,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       mbar_wait(&tfull_bar[g], (it >> 1) & 1);
       fence_after_sync();
+      const bool stamp = tm_ && half == 0 && q == 0 && lane == 0 && it < 20;
+      if (stamp) tm_[10 + 4 * it] = clock64();
       gt_epilogue<T, BN>(e, tmem_base + ((uint32_t)(q * 32) << 16) + g * BN, valid, m, orow, tile_n * BN, tile_n,
                          stg_base + (warp - 4) * GT_STG_WORDS, lane, half, bias_s);
       fence_before_sync();
       mbar_arrive(&tempty_bar[g]);
+      if (stamp) tm_[11 + 4 * it] = clock64();
+    }
     }
   }
   __syncthreads();

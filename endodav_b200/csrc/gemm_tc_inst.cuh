@@ -4,9 +4,26 @@
 #include "ops.h"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "gemm_bres.cuh"
 #include "conv_halo.cuh"
 
 namespace edv {
+
+// EDV_GEMM_TMA_OUT=0 falls back to the row-segment epilogue everywhere (A/B measurements)
+inline bool gemm_tma_out_enabled() {
+  static const bool v = [] { const char* e = getenv("EDV_GEMM_TMA_OUT"); return !(e && e[0] == '0'); }();
+  return v;
+}
+// the TMA-store epilogue handles 16-bit row-major outputs with bias / GELU / ReLU only
+inline bool gemm_tma_out_ok(const GemmArgs& a) {
+  using namespace tc;
+  const int k = a.e.kind;
+  if (!gemm_tma_out_enabled() || a.conv || k < 0) return false;
+  if (k != 0 && k != EF_BIAS && k != (EF_BIAS | EF_GELU) && k != (EF_BIAS | EF_RELU)) return false;
+  if (a.e.map != MAP_LINEAR || a.e.out_f32 || !a.e.out) return false;
+  if ((a.e.ldo * 2) % 16 != 0 || ((uintptr_t)a.e.out & 15) != 0) return false;
+  return true;
+}
 
 template <typename T, int BN, int BK, bool CONV>
 void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
@@ -38,6 +55,17 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
     uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
     if (!make_tmap(L, &tmB, dtype, a.W, 2, dims, str, box, swz)) return;
   }
+  // TMA-store epilogue: output tensor map over C [M rows, N cols] (row pitch ldo), box 16 columns x 128 rows, 32B swizzle
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof tmC);
+  GemmArgs a2 = a;
+  if (!CONV && BN % 64 == 0 && gemm_tma_out_ok(a)) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.e.ldo * 2};
+    uint32_t box[2] = {16u, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmC, dtype, a.e.out, 2, dims, str, box, 32)) return;
+    a2.e.kind |= tc::EF_TMA_OUT;
+  }
   const int kblocks = a.K / BK;
   const int stage_bytes = gt_stage_bytes<BN, BK>();
   const size_t stg_bytes = 16 * (size_t)GT_STG_WORDS * 4 + 16 * 128 * 4;   // + per-warp bias slices   // epilogue transposition buffers
@@ -57,7 +85,7 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
   const int grid = (int)std::min<long long>(total, num_sms());
   (void)kblocks;
   note_gemm(L, a, 2);
-  kern<<<grid, GT_THREADS, smem, L.stream>>>(tmA, tmB, a.e, a.M, a.N, a.K, stages, ct, n_tiles, (int)total);
+  kern<<<grid, GT_THREADS, smem, L.stream>>>(tmA, tmB, tmC, a2.e, a.M, a.N, a.K, stages, ct, n_tiles, (int)total);
   L.check("gemm_tc");
 }
 
@@ -168,8 +196,67 @@ template <typename T, bool CONV> void launch_gemm_tc_any(Launch& L, int dtype, c
 }
 
 #ifdef EDV_GEMM_TU_LIN
+// B-resident GEMM (gemm_bres.cuh): short K, 16-bit output through the TMA-store epilogue
+inline bool gemm_bres_enabled() {
+  static const bool v = [] { const char* e = getenv("EDV_GEMM_BRES"); return !(e && e[0] == '0'); }();
+  return v;
+}
+constexpr size_t GB_SMEM_MAX = 232448 - 1024;   // 227 KB opt-in limit minus the alignment slack
+
+template <typename T, int BN> bool launch_gemm_bres(Launch& L, int dtype, const GemmArgs& a) {
+  using namespace tc;
+  const int kblocks = a.K / 64;
+  const size_t b_bytes = (size_t)kblocks * BN * 128;
+  const size_t fixed = b_bytes + 4 * GT_OUT_SUB_BYTES + 4 * 64 * 4 + 512;
+  if (fixed + 2 * GB_A_STAGE > GB_SMEM_MAX) return false;
+  int stages = (int)((GB_SMEM_MAX - fixed) / GB_A_STAGE);
+  if (stages > 8) stages = 8;
+  CUtensorMap tmA, tmB, tmC;
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.lda * 2};
+    uint32_t box[2] = {64u, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmA, dtype, a.A, 2, dims, str, box, 128)) return true;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    uint64_t str[1] = {(uint64_t)a.K * 2};
+    uint32_t box[2] = {64u, (uint32_t)BN};
+    if (!make_tmap(L, &tmB, dtype, a.W, 2, dims, str, box, 128)) return true;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t str[1] = {(uint64_t)a.e.ldo * 2};
+    uint32_t box[2] = {16u, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmC, dtype, a.e.out, 2, dims, str, box, 32)) return true;
+  }
+  auto kern = gemm_bres_kernel<T, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    attr_done = true;
+  }
+  const int n_tiles = a.N / BN;
+  const int m_tiles = (a.M + GT_BM - 1) / GT_BM;
+  int grid = num_sms();
+  if (grid < n_tiles) return false;
+  if ((long long)m_tiles * n_tiles < grid) grid = std::max(n_tiles, m_tiles * n_tiles);
+  const size_t smem = fixed + (size_t)stages * GB_A_STAGE + 1024;
+  GemmArgs a2 = a;
+  a2.e.kind |= EF_TMA_OUT;
+  note_gemm(L, a, 2);
+  kern<<<grid, GB_THREADS, smem, L.stream>>>(tmA, tmB, tmC, a2.e, a.M, a.K, stages, n_tiles, m_tiles);
+  L.check("gemm_bres");
+  return true;
+}
+
 // linear GEMMs (2-D A operand)
 template <typename T> void launch_gemm_tc_lin(Launch& L, int dtype, const GemmArgs& a) {
+  if (gemm_bres_enabled() && gemm_tma_out_ok(a) && a.K % 64 == 0 && a.K <= 384 && a.lda == a.K && a.M >= 2048) {
+    if (a.N % 192 == 0) { if (launch_gemm_bres<T, 192>(L, dtype, a)) return; }
+    else if (a.N % 128 == 0) { if (launch_gemm_bres<T, 128>(L, dtype, a)) return; }
+    else if (a.N % 64 == 0) { if (launch_gemm_bres<T, 64>(L, dtype, a)) return; }
+  }
   if (gemm_2sm_min_m() > 0 && a.M >= gemm_2sm_min_m() && a.K % 64 == 0 && a.lda == a.K && a.e.act != ACT_GEGLU &&
       a.e.act != ACT_HEAD) {
     if (a.N % 256 == 0) return launch_gemm_tc2<T, 256>(L, dtype, a);

@@ -75,6 +75,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): the shared-memory ring of a TMA-fed kernel holds
+// 64-120 KB, which covers only ~1.1 us x 60 B/cycle of HBM latency; prefetching the boxes a few tiles / k-blocks ahead
+// into L2 lets the ring cover L2 latency instead (in-kernel timelines: k-blocks arrived every ~600 cycles against
+// 384 cycles of MMA because every first touch of an A tile went to HBM).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
   asm volatile(

@@ -30,7 +30,7 @@ typedef struct edv_ctx edv_ctx;
 /* Bumped whenever an entry point's argument list or a struct layout changes.  The ctypes host
  * (endodav_b200/engine.py) mirrors the signatures by hand, so it refuses a library whose
  * edv_abi_version() differs from its own constant instead of calling it with a stale layout. */
-#define EDV_ABI_VERSION 6
+#define EDV_ABI_VERSION 7
 int edv_abi_version(void);
 
 enum edv_status {
@@ -147,6 +147,11 @@ int edv_plan_buffer(edv_ctx* ctx, int index, char* name, int name_cap, size_t* o
  * Replaces: every nn.Linear / 1x1 conv on the path (attention.py:58,67; mlp.py:34-37; ...). */
 int edv_op_linear(int dtype, int engine, const void* A, const void* W, const float* bias, void* C, int M, int N, int K,
                   int act, void* stream);
+
+/* edv_op_linear on the tcgen05 kernel (16-bit dtypes) that also records the kernel's own timeline: 4 CTAs x 256 clock64
+ * stamps (per-tile accumulator-free / issued / complete / stored times, slot table in csrc/gemm_tc.cuh). */
+int edv_op_linear_timeline(int dtype, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act,
+                           long long* timeline_dev, void* stream);
 
 /* 3x3 convolution, padding 1, stride 1, NHWC: X[F,H,W,Cin] * Wt[Cout, 9*Cin] (+bias),
  * pre_relu applies ReLU to X first (ResidualConvUnit, util/blocks.py:78-84).

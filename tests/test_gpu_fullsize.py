@@ -198,9 +198,11 @@ def _scaled_packed(packed, s, depth, D):
     function unchanged but makes 16-bit intermediates s times larger: LayerNorm outputs (xn, the four taps) via
     gamma / beta * s with the consuming weight matrices / s; V and the attention output via the V bias * s (the V
     rows keep their weights) with proj.w / s.  Powers of two commute with fp16 rounding, so the fp16 result must
-    be BIT-IDENTICAL unless an activation overflows.  Weights whose scaled value would be an fp16 subnormal are
-    flushed to zero in both versions (a down-scaled weight would otherwise lose mantissa bits, which is a property of
-    this test's re-parameterisation, not of the network).  Returns (base, scaled)."""
+    be the unscaled one unless an activation overflows -- up to fp16 SUBNORMAL effects: a few LayerNorm outputs below
+    6e-5 carry fewer mantissa bits in the unscaled run than in the scaled one, and those last-bit differences are
+    amplified like any other rounding noise (tools/scale_ops_diag.py: every kernel is scale-exact except for
+    subnormal outputs).  Weights whose scaled value would be an fp16 subnormal are flushed to zero in both versions.
+    Returns (base, scaled)."""
     tiny = s * 2.0 ** -14
     base = {k: v.clone() for k, v in packed.items()}
     down = ["proj%d.w" % i for i in range(4)]
@@ -232,7 +234,8 @@ def _scaled_packed(packed, s, depth, D):
 @pytest.mark.parametrize("scale", [8.0, 64.0])
 def test_fp16_scaled_operands_do_not_saturate(scale):
     """LN outputs, the four taps, V and the attention output scaled by 8x / 64x (DINOv2 checkpoints carry
-    large-magnitude channels): the fp16 path must stay finite and reproduce the unscaled fp16 result bit for bit."""
+    large-magnitude channels): the fp16 path must stay finite, nothing may come near the fp16 limit, and the result
+    must agree with the unscaled fp16 run to within fp16 rounding noise (the same gates as against the oracle)."""
     from endodav_b200 import pack
 
     ctor = dict(encoder="vits", features=64, out_channels=[48, 96, 192, 384], r=4, lora_type="dvlora",
@@ -259,5 +262,8 @@ def test_fp16_scaled_operands_do_not_saturate(scale):
     assert np.isfinite(got).all()
     for name, st in scan.items():
         assert st["nonfinite"] == 0, (name, st)
+        if not st["fp32"]:
+            assert st["over_3e4"] == 0, (name, st)
     assert float(np.abs(base).mean()) > 0.05
-    assert np.array_equal(got, base), float(rel.max())
+    absrel, a1 = _metrics(got, base)
+    assert rel.max() <= GATES["fp16"]["rel"] and absrel <= GATES["fp16"]["absrel"] and a1 >= GATES["fp16"]["a1"], (float(rel.max()), absrel, a1)

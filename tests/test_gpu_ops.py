@@ -231,7 +231,9 @@ def test_disp_head_fused(dtype, Fr, h, w, oh, ow, C, sig):
 
 def test_linear_2sm_kernel_matches_default():
     """The experimental cta_group::2 GEMM (gemm_tc2.cuh, EDV_GEMM_2SM=<min M>) must agree bit for bit with
-    the default 1-SM kernel: same operands, same fp32 accumulation order per output element."""
+    the default 1-SM kernel: same operands, same fp32 accumulation order per output element (act = none: the two
+    kernels evaluate GELU with different, equally accurate formulas), and the TMA-store epilogue of the default
+    kernel must agree bit for bit with its row-segment epilogue (EDV_GEMM_TMA_OUT=0)."""
     import os
     import subprocess
     import sys
@@ -242,14 +244,15 @@ def test_linear_2sm_kernel_matches_default():
         "g = torch.Generator().manual_seed(3);"
         "A = (torch.randn(20000, 384, generator=g)).half().cuda(); W = (torch.randn(1152, 384, generator=g) * 0.05).half().cuda();"
         "b = torch.randn(1152, generator=g).cuda();"
-        "torch.save(eng.op_linear(A, W, b, 1).cpu(), sys.argv[1])" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        "torch.save(eng.op_linear(A, W, b, 0).cpu(), sys.argv[1])" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     outs = []
-    for v in ("0", "512"):
-        path = "/tmp/edv_lin_%s.pt" % v
-        env = dict(os.environ, EDV_GEMM_2SM=v)
+    for v, t in (("0", "1"), ("512", "1"), ("0", "0")):
+        path = "/tmp/edv_lin_%s_%s.pt" % (v, t)
+        env = dict(os.environ, EDV_GEMM_2SM=v, EDV_GEMM_TMA_OUT=t)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
         outs.append(torch.load(path))
     assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2])
 
 
 # ---- GPU-side preprocessing of the long-video driver ------------------------------------------------

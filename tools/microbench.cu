@@ -144,6 +144,150 @@ __global__ void __launch_bounds__(128, 1) mma_bench_uniform(long long* out, int 
   }
 }
 
+// ---- what slows tcgen05.mma down inside a real kernel? --------------------------------------------------------------
+// The MMA stream of a GEMM mainloop (M = 128, N = 192, SS operands, warp-uniform issue) measured (a) alone, (b) while
+// 16 other warps read a second accumulator with tcgen05.ld (the epilogue), (c) while a producer thread streams bulk
+// copies into other shared-memory stages (the TMA ring), (d) both.
+template <int N>
+__global__ void __launch_bounds__(640, 1) mma_contention(long long* out, int groups, int with_ld, int with_copy, const unsigned char* gsrc) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                 // 16 KB
+  unsigned char* sB = smem + 16384;         // 32 KB
+  unsigned char* sC = smem + 49152;         // 3 x 40 KB copy targets
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sC + 3 * 40960);
+  uint64_t* cbar = bar + 1;                 // 3 copy barriers
+  uint32_t* slot = reinterpret_cast<uint32_t*>(cbar + 3);
+  volatile int* stop = reinterpret_cast<volatile int*>(slot + 1);
+  for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&cbar[i], 1);
+    *stop = 0;
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  const int warp = threadIdx.x >> 5;
+  if (warp == 1) tmem_alloc(slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = *slot;
+  if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc<f16>(128, N, 0);
+    const uint64_t adesc = make_smem_desc(smem_u32(sA), 1024, 16, SWZ_128B);
+    const uint64_t bdesc = make_smem_desc(smem_u32(sB), 1024, 16, SWZ_128B);
+    const uint32_t leader = elect_one();
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(tm, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1);
+      }
+      __syncwarp();
+    }
+    if (leader) mma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (leader) out[blockIdx.x] = t1 - t0;
+    *stop = 1;
+  } else if (warp == 0) {
+    if (with_copy && threadIdx.x == 0) {
+      // stream 40 KB bulk copies global (L2 resident) -> shared, three in flight, until the MMA warp is done
+      uint32_t n = 0;
+      while (!*stop) {
+        const uint32_t s = n % 3;
+        if (n >= 3) mbar_wait(&cbar[s], ((n / 3) - 1) & 1);
+        mbar_expect_tx(&cbar[s], 40960);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sC + s * 40960)),
+                     "l"(gsrc + (size_t)((blockIdx.x * 7 + n) % 64) * 40960), "r"(40960), "r"(smem_u32(&cbar[s]))
+                     : "memory");
+        ++n;
+      }
+      for (uint32_t i = (n > 3 ? n - 3 : 0); i < n; ++i) mbar_wait(&cbar[i % 3], (i / 3) & 1);
+      out[1024 + blockIdx.x] = n;
+    }
+  } else if (warp >= 4 && with_ld) {
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    float acc = 0.f;
+    while (!*stop) {
+      float v[16];
+      tmem_ld16(tm + lane_off + 256 + ((warp - 4) >> 2) * 48, v);
+      acc += v[0];
+    }
+    if (acc == 12345.f) out[2048] = 1;
+  }
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tm, 512);
+  }
+}
+
+// ---- per-k-block bookkeeping of a GEMM mainloop: which part is not hidden behind the MMAs? -------------------------
+// groups of 4 MMAs (N = 192) with, per group: bit0 tcgen05.commit to an mbarrier, bit1 a wait on an already completed
+// mbarrier, bit2 tcgen05.fence::after_thread_sync, bit3 rebuilding the two shared-memory descriptors, bit4 the
+// accumulator alternates between TMEM columns 0 and 192 every 6 groups, bit5 the operands rotate over 4 A stages and
+// 6 resident B k-blocks (212 KB footprint, as in gemm_bres_kernel).
+__global__ void __launch_bounds__(128, 1) mma_loop_overheads(long long* out, int groups, int mode) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                 // 4 x 16 KB
+  unsigned char* sB = smem + 65536;         // 6 x 24 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 6 * 24576);
+  uint64_t* done_bar = bar + 1;     // completed once: waits with parity 0 succeed immediately
+  uint64_t* sink_bar = bar + 2;     // receives the per-group commits
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
+  for (int i = threadIdx.x; i < (65536 + 6 * 24576) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(done_bar, 1);
+    mbar_init(sink_bar, 1);
+    fence_barrier_init();
+    mbar_arrive(done_bar);
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) tmem_alloc(slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = *slot;
+  if ((threadIdx.x >> 5) == 1) {
+    constexpr uint32_t idesc = make_idesc<f16>(128, 192, 0);
+    const uint32_t leader = elect_one();
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    uint64_t adesc = make_smem_desc(a_addr, 1024, 16, SWZ_128B);
+    uint64_t bdesc = make_smem_desc(b_addr, 1024, 16, SWZ_128B);
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      if (mode & 2) mbar_wait(done_bar, 0);
+      if (mode & 4) fence_after_sync();
+      if (mode & 8) {
+        adesc = make_smem_desc(a_addr + ((mode & 32) ? (g & 3) * 16384 : 0), 1024, 16, SWZ_128B);
+        bdesc = make_smem_desc(b_addr + ((mode & 32) ? (g % 6) * 24576 : 0), 1024, 16, SWZ_128B);
+      }
+      const uint32_t d = tm + (((mode & 16) && ((g / 6) & 1)) ? 192 : 0);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1);
+        if (mode & 1) mma_commit(sink_bar);
+      }
+      __syncwarp();
+    }
+    if (leader) mma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (leader) out[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    fence_after_sync();
+    tmem_dealloc(tm, 512);
+  }
+}
+
 template <int N, bool TS, bool BMN, bool ALT> void run_mma_u(const char* what, long long* d_out, int nblocks) {
   auto kern = mma_bench_uniform<N, TS, BMN, ALT>;
   const int smem = 1024 + 16384 + 32768 + 64;
@@ -304,6 +448,45 @@ int main() {
     run_mma_u<64, true, true, false>("TS B MN-major", d_out, nb);
     run_mma_u<64, true, true, true>("TS B MN-major, alt D", d_out, nb);
     run_mma_u<32, false, false, true>("SS K-major, alt D", d_out, nb);
+  }
+  {
+    const int smem = 1024 + 65536 + 6 * 24576 + 128;
+    CK(cudaFuncSetAttribute(mma_loop_overheads, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int mode : {0, 15, 16, 8 + 32, 15 + 16 + 32}) {
+      const int groups = 512;
+      mma_loop_overheads<<<sms, 128, smem>>>(d_out, groups, mode);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> h(sms);
+      CK(cudaMemcpy(h.data(), d_out, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+      double s = 0;
+      for (long long v : h) s += (double)v;
+      printf("mma-loop N=192, per group of 4:%s%s%s%s%s -> %7.1f cycles per group (MMA alone: 384)\n", mode == 0 ? " nothing" : "",
+             (mode & 1) ? " commit" : "", (mode & 2) ? " wait(done)" : "", (mode & 4) ? " fence" : "", (mode & 8) ? " descriptors" : "",
+             s / sms / groups);
+      if (mode & 48) printf("      (+%s%s)\n", (mode & 16) ? " accumulator alternates between columns 0 / 192" : "", (mode & 32) ? " operands rotate over 4 A stages x 6 B blocks" : "");
+    }
+  }
+  {
+    unsigned char* gsrc;
+    CK(cudaMalloc(&gsrc, 64 * 40960));
+    CK(cudaMemset(gsrc, 0, 64 * 40960));
+    auto kern = mma_contention<192>;
+    const int smem = 1024 + 49152 + 3 * 40960 + 128;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int mode = 0; mode < 4; ++mode) {
+      const int groups = 512;
+      CK(cudaMemset(d_out, 0, 4096 * sizeof(long long)));
+      kern<<<sms, 640, smem>>>(d_out, groups, mode & 1, (mode >> 1) & 1, gsrc);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> h(2048);
+      CK(cudaMemcpy(h.data(), d_out, 2048 * sizeof(long long), cudaMemcpyDeviceToHost));
+      double s = 0, c = 0;
+      for (int i = 0; i < sms; ++i) { s += (double)h[i]; c += (double)h[1024 + i]; }
+      printf("mma-contention N=192 SS, %s%s: %7.1f cycles / MMA;  bulk copies per CTA %.0f (%.1f B/cycle/SM into smem)\n",
+             (mode & 1) ? "16 warps tcgen05.ld " : "", (mode & 2) ? "+ 40 KB bulk copies" : ((mode & 1) ? "" : "alone"), s / sms / (groups * 4),
+             c / sms, c / sms * 40960.0 / (s / sms));
+    }
+    CK(cudaFree(gsrc));
   }
   for (int w : {4, 8, 16}) {
     run_pipe<OP_EX2_F32>("ex2.f32", d_f, d_out, w);
