@@ -382,23 +382,45 @@ struct Fwd {
     void* ao = buf("ao");
     void* hb = buf("h");
     int tap_i = 0;
+    // ViT-S (D = 384) on the tensor-core path: proj / fc2 run as row-owning GEMMs whose epilogue also emits the
+    // LayerNorm'ed operand of the NEXT GEMM (gemm_ln.cuh), so only the very first norm1 and the four tap norms remain
+    // separate launches.  xn_ready: xn already holds norm1_i(x) (written by fc2 of block i-1).
+    const bool fuse_ln = tc() && gemm_ln_supported(dt, D, D) && gemm_ln_supported(dt, D, 4 * D);
+    bool xn_ready = false;
     for (int i = 0; i < g.depth && L.ok(); ++i) {
       const std::string n = "blk" + std::to_string(i) + ".";
-      layernorm(L, dt, x, wf(n + "ln1.w", D), wf(n + "ln1.b", D), xn, p.M, D, 1e-6f);
+      if (!xn_ready) layernorm(L, dt, x, wf(n + "ln1.w", D), wf(n + "ln1.b", D), xn, p.M, D, 1e-6f);
+      xn_ready = false;
       linear(xn, p.M, D, n + "qkv.w", 3 * D, ep(qkv, 3 * D, wf(n + "qkv.b", 3 * D)));
       attention(L, dt, eng, qkv, ao, p.BT, p.N, g.heads);
-      {
+      if (fuse_ln) {
+        // x += ls1(proj(ao)); xn = norm2(x)      (LayerScale folded into proj.w / proj.b)
+        L.tag = "blk.proj";
+        gemm_ln(L, dt, ao, wt(n + "proj.w", (size_t)D * D), wf(n + "proj.b", D), x, xn, wf(n + "ln2.w", D), wf(n + "ln2.b", D), 1e-6f,
+                (int)p.M, D, D, 1);
+        L.tag.clear();
+      } else {
         Epi e = ep(x, D, wf(n + "proj.b", D));  // LayerScale folded into proj.w / proj.b
         e.out_f32 = 1; e.res1 = x; e.res1_f32 = 1; e.ld_res1 = D;
         linear(ao, p.M, D, n + "proj.w", D, e);
+        layernorm(L, dt, x, wf(n + "ln2.w", D), wf(n + "ln2.b", D), xn, p.M, D, 1e-6f);
       }
-      layernorm(L, dt, x, wf(n + "ln2.w", D), wf(n + "ln2.b", D), xn, p.M, D, 1e-6f);
       {
         Epi e = ep(hb, 4 * D, wf(n + "fc1.b", 4 * D));  // LoRA merged into fc1.w (mylora/layers.py:384-393)
         e.act = ACT_GELU;
         linear(xn, p.M, D, n + "fc1.w", 4 * D, e);
       }
-      {
+      if (fuse_ln) {
+        // x += ls2(fc2(h)); xn = norm1 of the NEXT block, unless this block ends with a residual bottleneck (which
+        // changes x again) or is the last one
+        const bool next_ln = (i + 1 < g.depth) && !(g.res_blocks & (1 << i));
+        const std::string nn = "blk" + std::to_string(i + 1) + ".";
+        L.tag = "blk.fc2";
+        gemm_ln(L, dt, hb, wt(n + "fc2.w", (size_t)D * 4 * D), wf(n + "fc2.b", D), x, xn, next_ln ? wf(nn + "ln1.w", D) : nullptr,
+                next_ln ? wf(nn + "ln1.b", D) : nullptr, 1e-6f, (int)p.M, D, 4 * D, next_ln ? 1 : 0);
+        L.tag.clear();
+        xn_ready = next_ln;
+      } else {
         Epi e = ep(x, D, wf(n + "fc2.b", D));
         e.out_f32 = 1; e.res1 = x; e.res1_f32 = 1; e.ld_res1 = D;
         linear(hb, p.M, 4 * D, n + "fc2.w", D, e);
@@ -1026,6 +1048,17 @@ int edv_op_linear_timeline(int dtype, const void* A, const void* W, const float*
   a.e.tim = timeline_dev;
   if (const char* env = getenv("EDV_GEMM_DBG")) a.e.dbg = atoi(env);
   gemm(L, dtype, EDV_ENGINE_TC, a);
+  return finish(L);
+}
+
+int edv_op_linear_residual_ln(int dtype, const void* A, const void* W, const float* bias, float* x_inout, const float* gamma,
+                              const float* beta, float eps, void* xn_out, int M, int N, int K, long long* timeline_dev, void* stream) {
+  if (!A || !W || !x_inout || M < 1) return EDV_ERR_ARG;
+  Launch L;
+  L.stream = (cudaStream_t)stream;
+  const int do_ln = (gamma && beta && xn_out) ? 1 : 0;
+  if (timeline_dev && cudaMemsetAsync(timeline_dev, 0, 64 * sizeof(long long), L.stream) != cudaSuccess) return EDV_ERR_CUDA;
+  gemm_ln(L, dtype, A, W, bias, x_inout, xn_out, gamma, beta, eps, M, N, K, do_ln, timeline_dev);
   return finish(L);
 }
 

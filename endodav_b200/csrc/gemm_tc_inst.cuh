@@ -5,6 +5,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_bres.cuh"
+#include "gemm_ln.cuh"
 #include "conv_halo.cuh"
 
 namespace edv {
@@ -249,6 +250,66 @@ template <typename T, int BN> bool launch_gemm_bres(Launch& L, int dtype, const 
   L.check("gemm_bres");
   return true;
 }
+
+template <typename T>
+void launch_gemm_ln(Launch& L, int dtype, const void* A, const void* W, const float* bias, float* x, void* xn, const float* gamma,
+                    const float* beta, float eps, int M, int K, int do_ln, long long* tim) {
+  using namespace tc;
+  CUtensorMap tmA, tmB, tmX, tmXn;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {64u, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmA, dtype, A, 2, dims, str, box, 128)) return;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)GL_N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {64u, (uint32_t)GL_HN};
+    if (!make_tmap(L, &tmB, dtype, W, 2, dims, str, box, 128)) return;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)GL_N, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)GL_N * 4};
+    uint32_t box[2] = {16u, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmX, EDV_F32, x, 2, dims, str, box, 64)) return;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)GL_N, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)GL_N * 2};
+    uint32_t box[2] = {16u, (uint32_t)GT_BM};
+    if (!make_tmap(L, &tmXn, dtype, do_ln ? xn : (const void*)x, 2, dims, str, box, 32)) return;
+  }
+  auto kern = gemm_ln_kernel<T>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GL_SMEM);
+    attr_done = true;
+  }
+  const int m_tiles = (M + GT_BM - 1) / GT_BM;
+  const int grid = 2 * std::min(m_tiles, num_sms() / 2);   // clusters of two CTAs, one 128-row tile per pair at a time
+  // algorithmic work: 2 M N K; bytes: A + W + the fp32 stream read and written once + xn written once
+  L.note(2.0 * M * GL_N * K, ((double)M * K + (double)GL_N * K) * 2 + (double)M * GL_N * (8 + (do_ln ? 2 : 0)));
+  kern<<<grid, GL_THREADS, GL_SMEM, L.stream>>>(tmA, tmB, tmX, tmXn, bias, gamma, beta, eps, M, K, m_tiles, do_ln, tim);
+  L.check("gemm_ln");
+}
+
+#ifdef EDV_GEMM_LN_DEFS
+inline bool gemm_ln_enabled() {
+  static const bool v = [] { const char* e = getenv("EDV_GEMM_LN"); return !(e && e[0] == '0'); }();
+  return v;
+}
+bool gemm_ln_supported(int dtype, int N, int K) {
+  return gemm_ln_enabled() && dtype != EDV_F32 && N == tc::GL_N && K % 64 == 0 && K >= 64;
+}
+void gemm_ln(Launch& L, int dtype, const void* A, const void* W, const float* bias, float* x, void* xn, const float* gamma,
+             const float* beta, float eps, int M, int N, int K, int do_ln, long long* tim) {
+  if (!L.ok()) return;
+  if (!gemm_ln_supported(dtype, N, K)) return L.fail(EDV_ERR_ARG, "gemm_ln: needs a 16-bit dtype, N == 384 and K % 64 == 0");
+  if (dtype == EDV_BF16) launch_gemm_ln<bf16>(L, dtype, A, W, bias, x, xn, gamma, beta, eps, M, K, do_ln, tim);
+  else launch_gemm_ln<f16>(L, dtype, A, W, bias, x, xn, gamma, beta, eps, M, K, do_ln, tim);
+}
+#endif
 
 // linear GEMMs (2-D A operand)
 template <typename T> void launch_gemm_tc_lin(Launch& L, int dtype, const GemmArgs& a) {

@@ -38,7 +38,7 @@ inline PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-// rank-R tiled map over a 16-bit tensor; dims/box innermost first; strides in bytes for dims 1..R-1
+// rank-R tiled map over a 16-bit (or, dtype == EDV_F32, float32) tensor; dims/box innermost first; strides in bytes for dims 1..R-1
 inline bool make_tmap(Launch& L, CUtensorMap* m, int dtype, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   PFN_tmapEncodeTiled fn = get_encode_fn();
@@ -59,7 +59,9 @@ inline bool make_tmap(Launch& L, CUtensorMap* m, int dtype, const void* base, in
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUtensorMapDataType dt = dtype == EDV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMapDataType dt = dtype == EDV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                           : dtype == EDV_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                              : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -126,6 +128,10 @@ inline void pick_conv_tile(int H, int W, int* th, int* tw) {
 // gemm_tc_lin_{f16,bf16}.cu / gemm_tc_conv_{f16,bf16}.cu: tcgen05 GEMM and implicit-GEMM 3x3 conv
 template <typename T> void launch_gemm_tc_lin(Launch& L, int dtype, const GemmArgs& a);
 template <typename T> void launch_gemm_tc_conv(Launch& L, int dtype, const GemmArgs& a);
+// gemm_tc_lin_*.cu: x += A W^T + bias (fp32, in place) fused with xn = LayerNorm(x) (gemm_ln.cuh; N = 384 only)
+bool gemm_ln_supported(int dtype, int N, int K);
+void gemm_ln(Launch& L, int dtype, const void* A, const void* W, const float* bias, float* x, void* xn, const float* gamma,
+             const float* beta, float eps, int M, int N, int K, int do_ln, long long* tim = nullptr);
 // attention.cu: spatial flash attention (tcgen05) / CUDA-core attention, temporal attention
 void attention(Launch& L, int dtype, int engine, const void* qkv, void* out, int F, int S, int heads,
                long long* timeline = nullptr);

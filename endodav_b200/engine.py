@@ -16,7 +16,7 @@ DTYPES = {"fp32": EDV_F32, "f32": EDV_F32, "float32": EDV_F32, "bf16": EDV_BF16,
           "fp16": EDV_F16, "f16": EDV_F16, "float16": EDV_F16}
 TORCH_DTYPE = {EDV_F32: torch.float32, EDV_BF16: torch.bfloat16, EDV_F16: torch.float16}
 
-ABI_VERSION = 7   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
+ABI_VERSION = 9   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
 
 EXPORTS = [
     "edv_abi_version", "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
@@ -24,7 +24,7 @@ EXPORTS = [
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
     "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
     "edv_op_disp_head", "edv_op_cubic_resize_u8", "edv_op_stitch_window", "edv_op_stitch_plan",
-    "edv_op_disp_to_depth", "edv_op_compute_errors", "edv_op_attention_timeline", "edv_op_linear_timeline",
+    "edv_op_disp_to_depth", "edv_op_compute_errors", "edv_op_attention_timeline", "edv_op_linear_timeline", "edv_op_linear_residual_ln",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library():
     lib.edv_op_linear.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.edv_op_conv3x3.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.edv_op_attention.argtypes = [ci, ci, vp, vp, ci, ci, ci, vp]
+    lib.edv_op_linear_residual_ln.argtypes = [ci, vp, vp, vp, vp, vp, vp, ctypes.c_float, vp, ci, ci, ci, vp, vp]
     lib.edv_op_linear_timeline.argtypes = [ci, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]
     lib.edv_op_attention_timeline.argtypes = [ci, vp, vp, ci, ci, ci, vp, vp]
     lib.edv_op_temporal_attention.argtypes = [ci, vp, vp, ci, ci, ci, ci, vp]
@@ -272,6 +273,18 @@ def op_linear(A, W, bias=None, act=0, engine=ENGINE_TC):
     C = torch.empty(M, N, dtype=A.dtype, device=A.device)
     _check(lib.edv_op_linear(_dt(A), engine, _ptr(A), _ptr(W), _ptr(bias), _ptr(C), M, N, K, act, _stream()), None, "edv_op_linear")
     return C
+
+
+def op_linear_residual_ln(A, W, bias, x, gamma=None, beta=None, eps=1e-6, timeline=None):
+    """x (float32 [M,384], updated IN PLACE) += A W^T + bias; returns LayerNorm(x) in A's dtype (None without gamma).
+    timeline: optional int64 [64] device tensor receiving the kernel's own epilogue time stamps."""
+    lib = load_library()
+    M, K = A.shape
+    N = W.shape[0]
+    xn = torch.empty(M, N, dtype=A.dtype, device=A.device) if gamma is not None else None
+    _check(lib.edv_op_linear_residual_ln(_dt(A), _ptr(A), _ptr(W), _ptr(bias), _ptr(x), _ptr(gamma), _ptr(beta), ctypes.c_float(eps),
+                                         _ptr(xn), M, N, K, _ptr(timeline), _stream()), None, "edv_op_linear_residual_ln")
+    return xn
 
 
 def op_linear_timeline(A, W, bias=None, act=0):

@@ -30,7 +30,7 @@ typedef struct edv_ctx edv_ctx;
 /* Bumped whenever an entry point's argument list or a struct layout changes.  The ctypes host
  * (endodav_b200/engine.py) mirrors the signatures by hand, so it refuses a library whose
  * edv_abi_version() differs from its own constant instead of calling it with a stale layout. */
-#define EDV_ABI_VERSION 7
+#define EDV_ABI_VERSION 9
 int edv_abi_version(void);
 
 enum edv_status {
@@ -152,6 +152,14 @@ int edv_op_linear(int dtype, int engine, const void* A, const void* W, const flo
  * stamps (per-tile accumulator-free / issued / complete / stored times, slot table in csrc/gemm_tc.cuh). */
 int edv_op_linear_timeline(int dtype, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act,
                            long long* timeline_dev, void* stream);
+
+/* Row-owning GEMM with fused residual add and LayerNorm (ViT-S, N = 384 only; 16-bit dtypes):
+ *   x_inout[M,N] (float32, in place) += A[M,K] W[N,K]^T + bias;  xn_out[M,N] (`dtype`) = LayerNorm(x; gamma, beta, eps).
+ * gamma / beta / xn_out NULL: residual update only.  timeline_dev: optional 64 clock64 stamps of the first cluster's
+ * epilogue (slot table in csrc/gemm_ln.cuh), else NULL.  Replaces `x = x + ls(proj(.))` / `x = x + ls(fc2(.))` followed by
+ * the next norm (layers/block.py:110-116,143-145; LayerScale is folded into W / bias by pack.py). */
+int edv_op_linear_residual_ln(int dtype, const void* A, const void* W, const float* bias, float* x_inout, const float* gamma,
+                              const float* beta, float eps, void* xn_out, int M, int N, int K, long long* timeline_dev, void* stream);
 
 /* 3x3 convolution, padding 1, stride 1, NHWC: X[F,H,W,Cin] * Wt[Cout, 9*Cin] (+bias),
  * pre_relu applies ReLU to X first (ResidualConvUnit, util/blocks.py:78-84).

@@ -270,3 +270,26 @@ def test_cubic_resize_u8_matches_cv2(N, H, W, h, w):
     assert got.shape == ref.shape
     # same arithmetic, different association / FMA contraction than OpenCV's SIMD loops: <= 2e-6 on values in [-0.2, 1.2]
     assert float(np.abs(got - ref).max()) <= 2e-6, float(np.abs(got - ref).max())
+
+
+# ---- row-owning GEMM + residual + LayerNorm (gemm_ln.cuh) ---------------------------------------------
+@pytest.mark.parametrize("dtype", DT16)
+@pytest.mark.parametrize("M,K", [(128, 384), (300, 384), (2568, 1536), (1370 * 4 + 7, 384), (20000, 1536)])
+def test_linear_residual_layernorm(dtype, M, K):
+    """x += A W^T + b (fp32, in place) and xn = LayerNorm(x) against float64 torch on the same 16-bit operands."""
+    N = 384
+    A, W = _rand((M, K), dtype, 11), _rand((N, K), dtype, 12, K ** -0.5)
+    b = _rand((N,), torch.float32, 13, 0.1)
+    x0 = _rand((M, N), torch.float32, 14, 3.0)
+    gam = (_rand((N,), torch.float32, 15, 0.1) + 1.0)
+    bet = _rand((N,), torch.float32, 16, 0.05)
+    x = x0.clone()
+    xn = eng.op_linear_residual_ln(A, W, b, x, gam, bet, 1e-6)
+    ref_x = x0.double() + F.linear(A.double(), W.double(), b.double())
+    assert float((x.double() - ref_x).abs().max()) <= 2e-5 * max(1.0, float(ref_x.abs().max()))
+    ref_n = F.layer_norm(ref_x, (N,), gam.double(), bet.double(), 1e-6)
+    _close(xn, ref_n.float(), dtype, "gemm_ln xn %s" % dtype)
+    # residual-only form
+    x2 = x0.clone()
+    assert eng.op_linear_residual_ln(A, W, b, x2) is None
+    assert torch.equal(x2, x)
