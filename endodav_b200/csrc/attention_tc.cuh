@@ -43,12 +43,12 @@ constexpr int FA_BM = 128;      // query rows per tile
 constexpr int FA_BN = 128;      // keys per iteration
 constexpr int FA_HD = 64;
 constexpr int FA_STAGES = 4;
-constexpr int FA_THREADS = 384;
-constexpr int FA_POLY_DEFAULT = 0;   // measured: the polynomial path only adds issue pressure (0: all MUFU)
+constexpr int FA_POLY_DEFAULT = 0;   // every n-th pair of exponentials on the FMA pipe (0: all MUFU)
+constexpr int FA_SPLIT_DEFAULT = 1;  // softmax threads per query row (see the kernel header)
 constexpr uint32_t FA_TILE_BYTES = FA_BM * FA_HD * 2;  // 16 KB: one 128 x 64 16-bit tile
 constexpr int FA_QBUF = 2;           // Q double buffer (items i and i+1)
 constexpr int FA_STAGGER = 1000;     // cycles warpgroup B starts behind warpgroup A (see the header)
-constexpr size_t FA_SMEM = 1024 + (2 * FA_QBUF + 2 * FA_STAGES) * (size_t)FA_TILE_BYTES + 256;
+constexpr size_t FA_SMEM = 1024 + (2 * FA_QBUF + 2 * FA_STAGES) * (size_t)FA_TILE_BYTES + 256 + 6 * 1024;   // + barriers + row max / sum exchange
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -152,9 +152,19 @@ __device__ __forceinline__ FaItem fa_item(int w, int nx, int heads, int S) {
   return it;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // PM: every PM-th PAIR of exponentials is evaluated with ex2_poly2 on the FMA pipe (0: all MUFU).
-template <typename T, int PM>
-__global__ void __launch_bounds__(FA_THREADS, 1)
+// SPLIT: threads per query row.  1: two softmax warpgroups, thread = row (128 scores in registers).  2: FOUR softmax
+//     warpgroups (640 threads), a row's 128 scores are split between two threads of different warpgroups (same TMEM
+//     lane quarter); they exchange the row max through shared memory + a 64-thread named barrier once per key block
+//     and their partial row sums once per item.  Why: ONE warp sustains only ~13 cycles per MUFU instruction in this
+//     instruction mix (scoreboard round trips between ex2 and its consumers), so two warps per scheduler leave the MUFU
+//     pipe 35-40 % idle (measured: serialising the two warpgroups' exponential phases with named barriers changed
+//     nothing, 1 650-1 800 cycles per phase either way); four warps per scheduler cover it.
+template <typename T, int PM, int SPLIT>
+__global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
     flash_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, T* __restrict__ out, int S, int heads, int nx,
                               int total_items, long long* __restrict__ tim) {
   // tim: optional in-kernel timeline (clock64 stamps of the first 8 CTAs, 64 slots each; edv_op_attention_timeline):
@@ -178,6 +188,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   uint64_t* s_free = o_done + 2;                 // 2: warpgroup t holds S_t(j) in registers
   uint64_t* pv_done = s_free + 2;                // 2: O_t += P_t(j) V_j has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xch = reinterpret_cast<float*>(bars + 32);   // SPLIT == 2: row max [parity][tile][half][row], then row sum [tile][half][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = heads * FA_HD;
@@ -195,9 +206,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
+      mbar_init(&p_full[t], 128 * SPLIT);
       mbar_init(&o_done[t], 1);
-      mbar_init(&s_free[t], 128);
+      mbar_init(&s_free[t], 128 * SPLIT);
       mbar_init(&pv_done[t], 1);
     }
     fence_barrier_init();
@@ -211,7 +222,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
   if (tm_ && threadIdx.x == 0) tm_[1] = clock64();
 
   if (warp < 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // 640 threads launch with 96: frees 128 x 40 registers ...
    if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -323,16 +335,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
    }
   } else {
     // ===== softmax warpgroups =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int t = (warp - 4) >> 2;        // 0: tile A, 1: tile B
+    if (SPLIT == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // ... which is all the CTA pool holds: 512 x 8 <= 5120 (112 would wait forever)
+    constexpr int NC = FA_BN / SPLIT;     // scores per thread and key block
+    constexpr int OC = FA_HD / SPLIT;     // O columns per thread
+    const int g = (warp - 4) >> 2;        // softmax warpgroup
+    const int t = g & 1;                  // 0: tile A, 1: tile B
+    const int hh = g >> 1;                // which half of the row's columns (SPLIT == 2)
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;          // row inside the tile
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + t * FA_BN;
-    const uint32_t tO = tmem_base + lane_off + 256 + t * FA_HD;
-    const uint32_t tP = tmem_base + lane_off + 384 + t * 64;
+    const uint32_t tS = tmem_base + lane_off + t * FA_BN + hh * NC;
+    const uint32_t tO = tmem_base + lane_off + 256 + t * FA_HD + hh * OC;
+    const uint32_t tP = tmem_base + lane_off + 384 + t * 64 + hh * (NC / 2);
+    const int pair_bar = 1 + t * 4 + q;   // named barrier of the two warps that share these 32 rows
     constexpr float LOG2E = 1.4426950408889634f;
-    const bool stamp = tm_ && t == 0 && r == 0;
+    const bool stamp = tm_ && t == 0 && r == 0 && hh == 0;
     if (t == 1) {
       // start half a key block behind warpgroup A (see the header): the offset persists, both warpgroups run the same loop
       const long long c0 = clock64();
@@ -346,24 +364,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
       if (t >= im.nt) continue;
       const int row_base = im.f * S;
       float m_used = -INFINITY;           // max the exponentials are currently taken against (raw units)
-      float l = 0.f;
+      float l = 0.f;                      // (partial, SPLIT == 2) row sum
       for (int j = 0; j < n_iter; ++j, ++cnt) {
         mbar_wait(&s_full[t], cnt & 1);
         fence_after_sync();
         if (stamp && cnt == 0) tm_[2] = clock64();
-        uint32_t sv[128];
-        tmem_ld32_nowait(tS, sv);
-        tmem_ld32_nowait(tS + 32, sv + 32);
-        tmem_ld32_nowait(tS + 64, sv + 64);
-        tmem_ld32_nowait(tS + 96, sv + 96);
+        uint32_t sv[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c += 32) tmem_ld32_nowait(tS + c, sv + c);
         tmem_ld_wait();
         fence_before_sync();
         mbar_arrive(&s_free[t]);          // S_t(j) is in registers: the tensor core may overwrite it with the next S_t
         if (stamp && cnt == 5) tm_[44] = clock64();
-        const int valid = S - j * FA_BN;  // keys of this tile that belong to the frame
-        if (valid < FA_BN) {
+        const int valid = S - j * FA_BN - hh * NC;  // keys of this thread's columns that belong to the frame
+        if (valid < NC) {
 #pragma unroll
-          for (int i = 0; i < 128; ++i)
+          for (int i = 0; i < NC; ++i)
             if (i >= valid) sv[i] = 0xff800000u;  // -inf
         }
         // row max: 8 independent chains of 3-input maxima (FMNMX3)
@@ -371,14 +387,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
 #pragma unroll
         for (int i = 0; i < 8; ++i) pm[i] = max3(__uint_as_float(sv[i]), __uint_as_float(sv[8 + i]), __uint_as_float(sv[16 + i]));
 #pragma unroll
-        for (int i = 24; i < 120; i += 16) {
+        for (int i = 24; i < NC - 8; i += 16) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) pm[c] = max3(pm[c], __uint_as_float(sv[i + c]), __uint_as_float(sv[i + 8 + c]));
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) pm[c] = fmaxf(pm[c], __uint_as_float(sv[120 + c]));
-        const float mx = fmaxf(max3(pm[0], pm[1], pm[2]), fmaxf(max3(pm[3], pm[4], pm[5]), fmaxf(pm[6], pm[7])));
-        // lazy rescale: keep the old reference max unless the row max grew by more than 2^8
+        for (int c = 0; c < 8; ++c) pm[c] = fmaxf(pm[c], __uint_as_float(sv[NC - 8 + c]));
+        float mx = fmaxf(max3(pm[0], pm[1], pm[2]), fmaxf(max3(pm[3], pm[4], pm[5]), fmaxf(pm[6], pm[7])));
+        if (SPLIT == 2) {
+          // the other half of the row: parity double buffer, so one barrier per key block orders write -> read -> rewrite
+          float* xm = xch + ((cnt & 1) * 2 + t) * 256 + r;
+          xm[hh * 128] = mx;
+          named_bar_sync(pair_bar, 64);
+          mx = fmaxf(mx, xm[(hh ^ 1) * 128]);
+        }
+        // lazy rescale: keep the old reference max unless the row max grew by more than 2^8 (both halves of a row see
+        // the same mx and m_used, so they take the same decision)
         float factor = 1.f;
         const bool grow = mx > m_used + 8.f / LOG2E;
         if (grow) {
@@ -391,9 +415,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         const float neg = -m_used * LOG2E;
         if (stamp && cnt == 5) tm_[45] = clock64();
         float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;   // two packed partial row sums
-        uint32_t pv[64];
+        uint32_t pv[NC / 2];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < NC / 2; ++i) {
           float x0, x1, p0, p1;
           fma2_bcast(x0, x1, __uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1]), LOG2E, neg);
           if (PM > 0 && (i % (PM > 0 ? PM : 1)) == (PM > 0 ? PM - 1 : 0)) {
@@ -414,7 +438,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           if (stamp && cnt == 5) tm_[47] = clock64();
           if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
-            for (int c = 0; c < FA_HD; c += 32) {
+            for (int c = 0; c < OC; c += 32) {
               uint32_t ov[32];
               tmem_ld32_nowait(tO + c, ov);
               tmem_ld_wait();
@@ -425,8 +449,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
           }
         }
         // (j == 0: the last PV of this tile's previous item completed before its epilogue read O -- o_done)
-        tmem_st32(tP, pv);
-        tmem_st32(tP + 32, pv + 32);
+#pragma unroll
+        for (int c = 0; c < NC / 2; c += 32) tmem_st32(tP + c, pv + c);
         tmem_st_wait();
         fence_before_sync();
         mbar_arrive(&p_full[t]);
@@ -434,14 +458,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
         if (stamp && cnt < 16) tm_[3 + cnt] = clock64();
       }
       // ---- epilogue: O / l -> global ----
+      if (SPLIT == 2) {
+        // full row sum = the two halves' partial sums (the n_iter >= 1 row-max barriers since the previous item's
+        // exchange order the reuse of this buffer)
+        float* xl = xch + 1024 + t * 256 + r;
+        xl[hh * 128] = l;
+        named_bar_sync(pair_bar, 64);
+        l += xl[(hh ^ 1) * 128];
+      }
       mbar_wait(&o_done[t], items & 1);
       fence_after_sync();
       if (stamp && items == 0) tm_[20] = clock64();
       const float inv = 1.f / l;
       const int qi = im.q0 + t * FA_BM + r;
-      T* orow = out + ((long long)row_base + qi) * D + im.h * FA_HD;
+      T* orow = out + ((long long)row_base + qi) * D + im.h * FA_HD + hh * OC;
 #pragma unroll
-      for (int c = 0; c < FA_HD; c += 32) {
+      for (int c = 0; c < OC; c += 32) {
         uint32_t ov[32];
         tmem_ld32_nowait(tO + c, ov);
         tmem_ld_wait();
@@ -475,27 +507,30 @@ void launch_attention_tc(edv::Launch& L, int dtype, const void* qkv, void* out, 
   uint64_t str[1] = {(uint64_t)3 * D * 2};
   uint32_t box[2] = {(uint32_t)FA_HD, (uint32_t)FA_BM};
   if (!make_map(L, &tm, dtype, qkv, 2, dims, str, box, 128)) return;
-  // EDV_FA_POLY=<0|2|3|4>: every n-th pair of exponentials on the FMA pipe (tuning knob; 0 = all MUFU)
-  static int pm = -1;
+  // EDV_FA_POLY=<0|4|8>: every n-th pair of exponentials on the FMA pipe (0 = all MUFU); EDV_FA_SPLIT=<1|2>: threads per row
+  static int pm = -1, split = -1;
   if (pm < 0) {
     const char* env = getenv("EDV_FA_POLY");
     pm = env ? atoi(env) : FA_POLY_DEFAULT;
-    if (pm != 0 && pm != 2 && pm != 3 && pm != 4) pm = FA_POLY_DEFAULT;
+    if (pm != 0 && pm != 4 && pm != 8) pm = FA_POLY_DEFAULT;
+    const char* e2 = getenv("EDV_FA_SPLIT");
+    split = e2 ? atoi(e2) : FA_SPLIT_DEFAULT;
+    if (split != 1 && split != 2) split = FA_SPLIT_DEFAULT;
   }
-  void (*kern)(const CUtensorMap, T*, int, int, int, int, long long*) = pm == 0 ? flash_attention_tc_kernel<T, 0>
-                                                  : pm == 2 ? flash_attention_tc_kernel<T, 2>
-                                                  : pm == 3 ? flash_attention_tc_kernel<T, 3>
-                                                            : flash_attention_tc_kernel<T, 4>;
-  static bool attr_done[5] = {false, false, false, false, false};
-  if (!attr_done[pm]) {
+  void (*kern)(const CUtensorMap, T*, int, int, int, int, long long*) =
+      split == 1 ? flash_attention_tc_kernel<T, 0, 1>
+                 : pm == 0 ? flash_attention_tc_kernel<T, 0, 2> : pm == 4 ? flash_attention_tc_kernel<T, 4, 2> : flash_attention_tc_kernel<T, 8, 2>;
+  const int slot = split == 1 ? 0 : pm == 0 ? 1 : pm == 4 ? 2 : 3;
+  static bool attr_done[4] = {false, false, false, false};
+  if (!attr_done[slot]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM);
-    attr_done[pm] = true;
+    attr_done[slot] = true;
   }
   const int nx = (S + 2 * FA_BM - 1) / (2 * FA_BM);
   const long long total = (long long)nx * heads * F;
   if (total > 0x7fffffffLL) return L.fail(EDV_ERR_ARG, "flash_attention_tc: too many work items");
   const int grid = (int)std::min<long long>(total, edv::num_sms());
-  kern<<<grid, FA_THREADS, FA_SMEM, L.stream>>>(tm, (T*)out, S, heads, nx, (int)total, timeline);
+  kern<<<grid, 128 + 256 * split, FA_SMEM, L.stream>>>(tm, (T*)out, S, heads, nx, (int)total, timeline);
   L.check("flash_attention_tc");
 }
 

@@ -91,17 +91,22 @@ struct edv_ctx {
   static constexpr int GRAPH_SLOTS = 8;
   int graph_mode = 1;
   bool plan_warm = false;              // the first forward of a plan runs eagerly (one-time cudaFuncSetAttribute etc.)
-  int graph_misses = 0;                // consecutive captures without a replay: callers whose pointers never repeat run eagerly
   unsigned long long graph_clock = 0;
   std::vector<GraphEntry> graphs;
+  std::vector<GraphEntry> seen;        // pointer sets met once (no graph yet): a set is captured the SECOND time it comes by
+  cudaStream_t cap_stream = nullptr;   // private capture stream: the caller's stream may be the legacy default stream, which cannot be captured
+  std::string graph_note = "no capture attempted";   // why the last capture attempt did not produce a graph (edv_graph_status)
   void drop_graphs() {
     for (GraphEntry& g : graphs)
       if (g.exec) cudaGraphExecDestroy(g.exec);
     graphs.clear();
+    seen.clear();
     plan_warm = false;
-    graph_misses = 0;
   }
-  ~edv_ctx() { drop_graphs(); }
+  ~edv_ctx() {
+    drop_graphs();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
   Profiler prof;
   struct Agg {
     double ms = 0, flops = 0, bytes = 0;
@@ -832,19 +837,30 @@ static int forward_common(edv_ctx* ctx, const void* frames, bool u8, float* cons
   for (GraphEntry& g : ctx->graphs) {
     if (!g.same(key)) continue;
     g.last_use = ctx->graph_clock;
-    ctx->graph_misses = 0;
     ctx->last_launches = g.launches;
     if (cudaGraphLaunch(g.exec, st) != cudaSuccess) return set_err(ctx, EDV_ERR_CUDA, "edv_forward: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return EDV_OK;
   }
-  // a caller whose buffers never repeat (fresh tensors on every call with a cold allocator) would pay a capture per
-  // call: after a few consecutive misses run eagerly, and try again later
-  if (ctx->graph_misses >= 2 * edv_ctx::GRAPH_SLOTS) {
-    if (++ctx->graph_misses > 64) ctx->graph_misses = edv_ctx::GRAPH_SLOTS;
-    Fwd f(ctx, workspace_dev, st);
-    return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+  // A capture costs about as much as a forward at the reference's resolution, so a pointer set is captured only the
+  // SECOND time it comes by: a caller whose buffers never repeat (fresh tensors from a cold or fragmented allocator,
+  // outputs pinned by record_stream) runs eagerly and pays nothing, a steady caller replays from its third call on.
+  {
+    bool met = false;
+    for (GraphEntry& g : ctx->seen)
+      if (g.same(key)) {
+        met = true;
+        g = ctx->seen.back();
+        ctx->seen.pop_back();
+        break;
+      }
+    if (!met) {
+      key.last_use = ctx->graph_clock;
+      if (ctx->seen.size() >= 4 * (size_t)edv_ctx::GRAPH_SLOTS) ctx->seen.erase(ctx->seen.begin());
+      ctx->seen.push_back(key);
+      Fwd f(ctx, workspace_dev, st);
+      return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+    }
   }
-  ++ctx->graph_misses;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
     // the caller is capturing this stream itself: just record our launches into its graph
@@ -852,7 +868,19 @@ static int forward_common(edv_ctx* ctx, const void* frames, bool u8, float* cons
     Fwd f(ctx, workspace_dev, st);
     return f.run(frames, u8, disp, resized_dev, out_h, out_w);
   }
-  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+  // Capture on a private stream and replay on the caller's: the capture itself executes nothing, and the caller's
+  // stream is usually torch's current stream = the legacy default stream, which cudaStreamBeginCapture refuses.
+  if (!ctx->cap_stream && cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    ctx->graph_note = std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(cudaGetLastError());
+    ctx->cap_stream = nullptr;
+    ctx->graph_mode = 0;
+    Fwd f(ctx, workspace_dev, st);
+    return f.run(frames, u8, disp, resized_dev, out_h, out_w);
+  }
+  cudaStream_t cap = ctx->cap_stream;
+  cudaError_t be = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  if (be != cudaSuccess) {
+    ctx->graph_note = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(be);
     cudaGetLastError();
     Fwd f(ctx, workspace_dev, st);
     return f.run(frames, u8, disp, resized_dev, out_h, out_w);
@@ -860,17 +888,17 @@ static int forward_common(edv_ctx* ctx, const void* frames, bool u8, float* cons
   int rc;
   int launches = 0;
   {
-    Fwd f(ctx, workspace_dev, st);
+    Fwd f(ctx, workspace_dev, cap);
     rc = f.run(frames, u8, disp, resized_dev, out_h, out_w);
     launches = f.L.count;
   }
   cudaGraph_t graph = nullptr;
-  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
   if (rc != EDV_OK || ce != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
+    ctx->graph_note = rc != EDV_OK ? std::string("forward failed under capture: ") + ctx->err : std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
     cudaGetLastError();
-    if (rc != EDV_OK) return rc;
-    ctx->graph_mode = 0;   // capture is not possible in this process (e.g. a legacy-stream interaction): stay eager
+    ctx->graph_mode = 0;   // capture is not possible in this process: stay eager (and say why in edv_graph_status)
     Fwd f(ctx, workspace_dev, st);
     return f.run(frames, u8, disp, resized_dev, out_h, out_w);
   }
@@ -878,11 +906,13 @@ static int forward_common(edv_ctx* ctx, const void* frames, bool u8, float* cons
   const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
   if (ie != cudaSuccess || !exec) {
+    ctx->graph_note = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie);
     cudaGetLastError();
     ctx->graph_mode = 0;
     Fwd f(ctx, workspace_dev, st);
     return f.run(frames, u8, disp, resized_dev, out_h, out_w);
   }
+  ctx->graph_note = "ok";
   key.exec = exec;
   key.launches = launches;
   key.last_use = ctx->graph_clock;
@@ -910,6 +940,9 @@ int edv_set_graph_mode(edv_ctx* ctx, int on) {
 
 // number of captured graphs currently cached for this plan (tests / bench evidence)
 int edv_graph_count(const edv_ctx* ctx) { return ctx ? (int)ctx->graphs.size() : 0; }
+
+// "ok" after a successful capture, else the reason the last attempt fell back to eager launches
+const char* edv_graph_status(const edv_ctx* ctx) { return ctx ? ctx->graph_note.c_str() : "null context"; }
 
 int edv_forward(edv_ctx* ctx, const float* frames_dev, float* const disp_dev[4], float* resized_dev, int out_h,
                 int out_w, void* workspace_dev, void* stream) {

@@ -15,6 +15,10 @@
 //                IS the canonical no-swizzle K-major UMMA layout for any shift (SBO = halo row pitch)
 //   warps 5..12  producers: compute the 18 x 10 halo of the upsampled map straight into that
 //                shared-memory layout (4-deep ring), zero outside the image (conv padding)
+// Measured (round 2): staging the <= 20 x 12 source pixels of a tile in shared memory first (cp.async, double
+// buffered) and interpolating from there is SLOWER (615 vs 531 us at 32 x 296^2 -> 518^2): the ~9x re-fetch of source
+// pixels through L1/L2 is not what bounds the kernel; the producers' instruction stream is (ncu: 250 M instructions,
+// issue slots 45 % busy with only 8 producer warps, top stall long_scoreboard).
 #pragma once
 #include "tc_common.cuh"
 

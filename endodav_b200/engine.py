@@ -16,11 +16,11 @@ DTYPES = {"fp32": EDV_F32, "f32": EDV_F32, "float32": EDV_F32, "bf16": EDV_BF16,
           "fp16": EDV_F16, "f16": EDV_F16, "float16": EDV_F16}
 TORCH_DTYPE = {EDV_F32: torch.float32, EDV_BF16: torch.bfloat16, EDV_F16: torch.float16}
 
-ABI_VERSION = 9   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
+ABI_VERSION = 10   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
 
 EXPORTS = [
     "edv_abi_version", "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
-    "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_plan_buffer", "edv_set_graph_mode", "edv_graph_count", "edv_op_linear", "edv_op_conv3x3",
+    "edv_output_shape", "edv_launch_count", "edv_set_debug", "edv_debug_tap", "edv_plan_buffer", "edv_set_graph_mode", "edv_graph_count", "edv_graph_status", "edv_op_linear", "edv_op_conv3x3",
     "edv_op_attention", "edv_op_temporal_attention", "edv_op_layernorm", "edv_op_groupnorm", "edv_op_upsample",
     "edv_op_resize_f32", "edv_profile", "edv_profile_reset", "edv_profile_collect", "edv_profile_get",
     "edv_op_disp_head", "edv_op_cubic_resize_u8", "edv_op_stitch_window", "edv_op_stitch_plan",
@@ -77,6 +77,8 @@ def load_library():
     lib.edv_plan_buffer.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(sz), ctypes.POINTER(sz), ctypes.POINTER(ci)]
     lib.edv_set_graph_mode.argtypes = [vp, ci]
     lib.edv_graph_count.argtypes = [vp]
+    lib.edv_graph_status.argtypes = [vp]
+    lib.edv_graph_status.restype = ctypes.c_char_p
     lib.edv_profile.argtypes = [vp, ci]
     lib.edv_profile_reset.argtypes = [vp]
     lib.edv_profile_collect.argtypes = [vp]
@@ -103,7 +105,7 @@ def load_library():
     lib.edv_op_resize_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("edv_destroy", "edv_last_error"):
+        if name not in ("edv_destroy", "edv_last_error", "edv_graph_status"):
             fn.restype = ci
     lib.edv_op_stitch_plan.restype = ctypes.c_longlong
     _lib = lib
@@ -212,6 +214,9 @@ class Engine:
 
     def graph_count(self):
         return int(self.lib.edv_graph_count(self.ctx))
+
+    def graph_status(self):
+        return self.lib.edv_graph_status(self.ctx).decode()
 
     def launch_count(self):
         return int(self.lib.edv_launch_count(self.ctx))

@@ -30,7 +30,7 @@ typedef struct edv_ctx edv_ctx;
 /* Bumped whenever an entry point's argument list or a struct layout changes.  The ctypes host
  * (endodav_b200/engine.py) mirrors the signatures by hand, so it refuses a library whose
  * edv_abi_version() differs from its own constant instead of calling it with a stale layout. */
-#define EDV_ABI_VERSION 9
+#define EDV_ABI_VERSION 10
 int edv_abi_version(void);
 
 enum edv_status {
@@ -109,10 +109,13 @@ int edv_output_shape(const edv_ctx* ctx, int scale, int* h, int* w);
  * cudaGraphExec keyed by the external pointers of the call (frames, disp[], resized, workspace) and replays it on
  * later calls with the same pointers: no tensor-map encoding and one host launch instead of ~190 -- what the
  * reference's production resolution (224x280, evaluate_depth_video.py:86) needs, where the forward is launch bound.
- * Up to 8 pointer sets are cached per plan; edv_plan, edv_set_weight (new pointer) and edv_set_debug drop them;
+ * A pointer set is captured the second time it is seen (callers whose buffers never repeat stay eager); up to 8 are
+ * cached per plan (LRU); edv_plan, edv_set_weight (new pointer) and edv_set_debug drop them;
  * profiling (edv_profile) and debug taps run eagerly.  Default on (environment EDV_GRAPH=0 turns it off). */
 int edv_set_graph_mode(edv_ctx* ctx, int on);
 int edv_graph_count(const edv_ctx* ctx);
+/* "ok" after a successful capture, otherwise why the last attempt fell back to eager launches (never NULL). */
+const char* edv_graph_status(const edv_ctx* ctx);
 
 /* Number of kernels the last edv_forward launched (bench.py's gpu_launches). */
 int edv_launch_count(const edv_ctx* ctx);

@@ -234,3 +234,39 @@ def test_gpu_preprocessing_equals_host_preprocessing(monkeypatch):
     monkeypatch.setenv("ENDODAV_PREPROCESS", "host")
     b = model.infer_video_depth(v)
     assert float(np.abs(a - b).max()) <= 1e-4 * max(1.0, float(np.abs(b).max()))
+
+
+def test_cuda_graph_replay_on_default_stream_is_bit_identical():
+    """edv_forward captures the planned launch sequence (on its private capture stream, so torch's legacy default
+    stream works too) and replays it: same bits as eager launches, one graph per pointer set, and the graph sees
+    new input VALUES written into the same buffers."""
+    m, _ = load_case("fwd_vits_dvlora")
+    model, cfg, sd = _build(m["ctor"], m["weight_seed"], "fp16")
+    B, T, H, W = m["input"]
+    x = weights.make_frames(B, T, H, W, m["frame_seed"]).cuda()
+    h, w = m["ctor"]["image_shape"]
+    eng = model._ensure_engine(h // 14, w // 14)
+    eng.set_graph_mode(False)
+    eager = model(x)[("disp", 0)].clone()
+    assert eng.graph_count() == 0
+    eng.set_graph_mode(True)
+    outs = []
+    for _ in range(4):
+        o = model(x)
+        outs.append(o[("disp", 0)].clone())
+        del o
+    assert eng.graph_count() >= 1, eng.graph_status()
+    assert eng.graph_status() == "ok"
+    for o in outs:
+        assert torch.equal(o, eager)
+    x2 = weights.make_frames(B, T, H, W, m["frame_seed"] + 1).cuda()
+    eng.set_graph_mode(False)
+    eager2 = model(x2)[("disp", 0)].clone()
+    eng.set_graph_mode(True)
+    model(x)
+    x.copy_(x2)           # same pointer, new values
+    for _ in range(3):
+        got2 = model(x)[("disp", 0)].clone()
+    assert eng.graph_count() >= 1
+    assert torch.equal(got2, eager2)
+    assert not torch.equal(got2, eager)

@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "../endodav_b200/csrc/tc_common.cuh"
+#include "../endodav_b200/csrc/ops.h"
+#include "../endodav_b200/csrc/attention_tc.cuh"
 
 using namespace tc;
 
@@ -369,6 +371,63 @@ template <int OP> void run_pipe(const char* what, float* d_f, long long* d_out, 
          (double)c / instr_per_smsp, 32.0 * 4 * instr_per_smsp / (double)c);
 }
 
+
+// ---- the exponential phase of the flash-attention softmax, as an instruction mix ---------------------------------
+// Each thread owns NP pairs of scores in registers and runs, per "key block":  x = s * log2e - m (FFMA2), p = ex2(x)
+// (2 MUFU), row sum (FADD2), 16-bit pack (F2FP) -- attention_tc.cuh's loop.  MODE bit 0: drop the pack, bit 1: drop the
+// row sum, bit 2: every 4th pair through the FMA-pipe polynomial.  Reports cycles per MUFU warp-instruction per SMSP
+// (the pipe alone: 8.0), i.e. how close this mix can get to the MUFU roofline with 1 / 2 / 4 warps per scheduler.
+template <int NP, int MODE> __global__ void __launch_bounds__(512, 1) softmax_mix_bench(const float* in, float* out, long long* cyc, int iters) {
+  float sv[2 * NP];
+#pragma unroll
+  for (int i = 0; i < 2 * NP; ++i) sv[i] = in[(threadIdx.x * 2 * NP + i) & 4095];
+  float acc = 0.f;
+  uint32_t px = 0;
+  float neg = -1.0f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+    uint32_t pv[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float x0, x1, p0, p1;
+      fma2_bcast(x0, x1, sv[2 * i], sv[2 * i + 1], 1.4426950408889634f, neg);
+      if ((MODE & 4) && (i & 3) == 3) {
+        ex2_poly2(p0, p1, x0, x1);
+      } else {
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
+      if (!(MODE & 2)) {
+        if (i & 1) add2(ls2, ls3, p0, p1);
+        else add2(ls0, ls1, p0, p1);
+      } else {
+        ls0 = p0; ls1 = p1;
+      }
+      if (!(MODE & 1)) pv[i] = pack_pair(p0, p1, f16());
+      else pv[i] = __float_as_uint(p0) ^ __float_as_uint(p1);
+    }
+    acc += (ls0 + ls1) + (ls2 + ls3);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) px ^= pv[i];
+    neg = -1.0f - 1e-6f * (float)(px & 1);     // loop-carried: the compiler cannot hoist the block
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + __uint_as_float(px);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+template <int NP, int MODE> void run_softmax_mix(const char* what, const float* d_in, float* d_f, long long* d_out, int warps) {
+  const int iters = 256;
+  softmax_mix_bench<NP, MODE><<<1, warps * 32>>>(d_in, d_f, d_out, iters);
+  CK(cudaDeviceSynchronize());
+  long long c;
+  CK(cudaMemcpy(&c, d_out, sizeof c, cudaMemcpyDeviceToHost));
+  const double mufu_per_smsp = (double)iters * 2 * NP * ((MODE & 4) ? 0.75 : 1.0) * warps / 4.0;
+  printf("softmax-mix %-34s pairs/thread=%2d warps/SM=%2d: %6.2f cycles per MUFU per SMSP, %7.1f cycles per key block of %d scores/thread\n", what, NP,
+         warps, (double)c / mufu_per_smsp, (double)c / iters, 2 * NP);
+}
+
 // ---- tcgen05.ld / st ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1) tmem_bench(long long* out, float* sink, int iters, int nwarps_active) {
   __shared__ uint32_t slot;
@@ -419,7 +478,28 @@ __global__ void __launch_bounds__(256, 1) tmem_bench(long long* out, float* sink
   }
 }
 
-int main() {
+static void run_mix_all(float* d_f, long long* d_out) {
+  {
+    float* d_in;
+    CK(cudaMalloc(&d_in, 4096 * sizeof(float)));
+    std::vector<float> hin(4096);
+    for (int i = 0; i < 4096; ++i) hin[i] = -0.01f * (i % 97);
+    CK(cudaMemcpy(d_in, hin.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice));
+    for (int w : {4, 8, 16}) {
+      run_softmax_mix<64, 0>("ffma2 + 2 ex2 + fadd2 + f2fp", d_in, d_f, d_out, w);
+      run_softmax_mix<64, 1>("... without the pack", d_in, d_f, d_out, w);
+      run_softmax_mix<64, 2>("... without the row sum", d_in, d_f, d_out, w);
+      run_softmax_mix<64, 3>("ffma2 + 2 ex2 only", d_in, d_f, d_out, w);
+      run_softmax_mix<64, 4>("full mix, every 4th pair polynomial", d_in, d_f, d_out, w);
+      run_softmax_mix<32, 0>("full mix", d_in, d_f, d_out, w);
+      run_softmax_mix<32, 4>("full mix, every 4th pair polynomial", d_in, d_f, d_out, w);
+    }
+    CK(cudaFree(d_in));
+  }
+}
+
+int main(int argc, char** argv) {
+  const bool only_mix = argc > 1 && std::string(argv[1]) == "mix";   // tools/microbench mix: the softmax instruction mix only
   long long* d_out;
   float* d_f;
   CK(cudaMalloc(&d_out, 4096 * sizeof(long long)));
@@ -427,6 +507,11 @@ int main() {
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   printf("SMs: %d\n", sms);
+  if (only_mix) {
+    run_mix_all(d_f, d_out);
+    printf("done\n");
+    return 0;
+  }
   for (int nb : {1, sms}) {
     run_mma<32, false, false, false>("SS K-major", d_out, nb);
     run_mma<64, false, false, false>("SS K-major", d_out, nb);
@@ -498,6 +583,7 @@ int main() {
     run_pipe<OP_CVT_F16X2>("cvt.f16x2.f32", d_f, d_out, w);
     run_pipe<OP_FADD>("add.f32", d_f, d_out, w);
   }
+  run_mix_all(d_f, d_out);
   for (int w : {4, 8}) {
     const int iters = 512;
     tmem_bench<<<1, 256>>>(d_out, d_f, iters, w);
