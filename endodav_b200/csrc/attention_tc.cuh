@@ -161,8 +161,13 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 //     lane quarter); they exchange the row max through shared memory + a 64-thread named barrier once per key block
 //     and their partial row sums once per item.  Why: ONE warp sustains only ~13 cycles per MUFU instruction in this
 //     instruction mix (scoreboard round trips between ex2 and its consumers), so two warps per scheduler leave the MUFU
-//     pipe 35-40 % idle (measured: serialising the two warpgroups' exponential phases with named barriers changed
-//     nothing, 1 650-1 800 cycles per phase either way); four warps per scheduler cover it.
+//     pipe 35-40 % idle; four warps per scheduler can cover it (tools/microbench mix: 11.6 / 9.3 / 8.1 cycles per MUFU
+//     with 1 / 2 / 4 warps per scheduler).  MEASURED SLOWER (200 vs 172 us at 32 x 6 x 1370): the two tiles run in
+//     phase, so the four warps' exponentials coincide (1 800 cycles) and so do their longer non-MUFU phases (load 450,
+//     max + exchange 450, P store 250).  Forcing the tiles into anti-phase with a pair of named barriers around the
+//     exponentials (MUFU ping-pong, instructions pinned with data dependencies -- ptxas moves register-only code across
+//     BAR) gave 1 280-cycle phases but 198 us: a block then costs two exclusive phases plus the hand-over.  Kept as
+//     EDV_FA_SPLIT=2 for the record; the default is 1.
 template <typename T, int PM, int SPLIT>
 __global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
     flash_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, T* __restrict__ out, int S, int heads, int nx,

@@ -15,7 +15,7 @@ from endodav_b200 import engine as eng  # noqa: E402
 dt = torch.float16
 M = 32 * 1370
 g = torch.Generator().manual_seed(0)
-ALL = ["fc1", "qkv", "fc2", "attn", "rcu", "tattn", "head", "oc", "ln"]
+ALL = ["fc1", "qkv", "fc2", "attn", "rcu", "tattn", "head", "oc", "ln", "proj_ln", "fc2_ln", "ups"]
 
 
 def rnd(*s, scale=1.0):
@@ -39,6 +39,14 @@ def run(w):
         eng.op_conv3x3(rnd(32, 296, 296, 64), rnd(32, 576, scale=0.04), torch.zeros(32).cuda(), False)
     elif w == "tattn":
         eng.op_temporal_attention(rnd(32 * 5476, 192, scale=0.7), 1, 32, 5476, 64)
+    elif w == "proj_ln":   # blk.proj: x += A W^T + b (fp32 residual stream), LayerNorm(x) -> 16 bit, one kernel (gemm_ln.cuh)
+        eng.op_linear_residual_ln(rnd(M, 384), rnd(384, 384, scale=0.05), torch.zeros(384).cuda(), torch.randn(M, 384, generator=g).cuda(),
+                                  torch.ones(384).cuda(), torch.zeros(384).cuda())
+    elif w == "fc2_ln":
+        eng.op_linear_residual_ln(rnd(M, 1536), rnd(384, 1536, scale=0.03), torch.zeros(384).cuda(), torch.randn(M, 384, generator=g).cuda(),
+                                  torch.ones(384).cuda(), torch.zeros(384).cuda())
+    elif w == "ups":       # fusion-block upsample 148^2 -> 296^2, 64 channels
+        eng.op_upsample(rnd(32, 148, 148, 64), 296, 296)
     elif w == "ln":
         eng.op_layernorm(torch.randn(M, 384, generator=g).cuda(), torch.ones(384).cuda(), torch.zeros(384).cuda(), 1e-6, dt)
     else:

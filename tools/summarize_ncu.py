@@ -60,10 +60,13 @@ WANT = [
 ]
 
 
-OPS = ["fc1", "qkv", "fc2", "attn", "rcu", "tattn", "head", "oc", "ln"]   # tools/prof_ops.py order (--range mode)
-CALLSITE = {"fc1": "gemm_tc:blk.fc1", "qkv": "gemm_tc:blk.qkv", "fc2": "gemm_tc:blk.fc2", "attn": "flash_attention_tc",
+import os
+# tools/prof_ops.py order (--range mode); EDV_PROF_OPS="fc1 qkv ..." names the ops of the capture being summarised
+OPS = (os.environ.get("EDV_PROF_OPS") or "fc1 qkv fc2 attn rcu tattn head oc ln").split()
+# bench.py call-site names of the round-2 engine (fc1 / qkv: B-resident GEMM, proj / fc2: GEMM + residual + LayerNorm)
+CALLSITE = {"fc1": "gemm_bres:blk.fc1", "qkv": "gemm_bres:blk.qkv", "fc2": "gemm_tc:blk.fc2(unfused)", "attn": "flash_attention_tc",
             "rcu": "conv_halo:ref.rcu.c1", "tattn": "temporal_attention", "head": "head_fused:oc2a", "oc": "conv_halo:oc1",
-            "ln": "layernorm"}
+            "ln": "layernorm", "proj_ln": "gemm_ln:blk.proj", "fc2_ln": "gemm_ln:blk.fc2", "ups": "upsample"}
 
 
 def full(src, dst):
@@ -72,7 +75,7 @@ def full(src, dst):
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
-    ours = re.compile(r"gemm_tc|flash_attention|temporal_attention|head_fused|conv3x3_halo|layernorm_kernel|groupnorm|upsample_nhwc|preprocess_patches|stitch_")
+    ours = re.compile(r"gemm_tc|gemm_bres|gemm_ln|flash_attention|temporal_attention|head_fused|conv3x3_halo|layernorm_kernel|groupnorm|upsample_nhwc|preprocess_patches|stitch_")
     data = [d for d in data if ours.search(d[ki])]   # drop torch's own fill / RNG kernels from the captured range
     # DRAM traffic per launch, keyed by bench.py's call-site names (one profiled launch per op, in OPS order)
     traffic = {}
