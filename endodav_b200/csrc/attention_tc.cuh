@@ -172,6 +172,7 @@ template <typename T, int PM, int SPLIT>
 __global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
     flash_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, T* __restrict__ out, int S, int heads, int nx,
                               int total_items, long long* __restrict__ tim) {
+  pdl_launch();   // PDL: the next kernel of the stream may start its prologue (common.cuh)
   // tim: optional in-kernel timeline (clock64 stamps of the first 8 CTAs, 64 slots each; edv_op_attention_timeline):
   // 0 entry, 1 setup done, 2 first S ready, 3+j end of softmax iteration j of the FIRST item (tile A), 20 its O complete,
   // 21 stored, 24+j PV(j) issued, 44..48 phases of iteration 5 (S loaded, max, exps, PV(j-1) done, P stored),
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // PDL: everything above ran under the previous kernel's tail; its results are visible from here
   if (tm_ && threadIdx.x == 0) tm_[1] = clock64();
 
   if (warp < 4) {
@@ -535,7 +537,7 @@ void launch_attention_tc(edv::Launch& L, int dtype, const void* qkv, void* out, 
   const long long total = (long long)nx * heads * F;
   if (total > 0x7fffffffLL) return L.fail(EDV_ERR_ARG, "flash_attention_tc: too many work items");
   const int grid = (int)std::min<long long>(total, edv::num_sms());
-  kern<<<grid, 128 + 256 * split, FA_SMEM, L.stream>>>(tm, (T*)out, S, heads, nx, (int)total, timeline);
+  edv::launch_k(kern, dim3(grid), dim3(128 + 256 * split), FA_SMEM, L.stream, tm, (T*)out, S, heads, nx, (int)total, timeline);
   L.check("flash_attention_tc");
 }
 

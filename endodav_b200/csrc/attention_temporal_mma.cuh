@@ -75,6 +75,8 @@ template <int HD> constexpr size_t ta_smem_per_pos() { return (size_t)(3 * 32 * 
 template <typename T, int HD, int PB>
 __global__ void __launch_bounds__(TA_WARPS * 32) temporal_attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn,
                                                                                int hw, const float2* __restrict__ rope) {
+  pdl_launch();
+  pdl_wait();
   constexpr int C = 8 * HD, ROW = ta_row<HD>();
   constexpr int CPS = C / 8;            // 16-byte chunks per q / k / v segment
   constexpr int CPR = 3 * CPS;          // chunks per (frame, position) row

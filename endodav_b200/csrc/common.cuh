@@ -11,6 +11,16 @@ typedef __half f16;
 // ---------------------------------------------------------------------------------------
 // element conversion
 // ---------------------------------------------------------------------------------------
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// Every kernel of the forward starts with pdl_launch() -- "the next kernel of the stream may be scheduled now" -- and
+// calls pdl_wait() before its first access to global memory: the wait returns when the PREVIOUS kernel of the stream
+// has completed and its writes are visible.  The next kernel's CTAs therefore become resident, run their prologue
+// (barrier init, TMEM allocation, tensor-map prefetch, index arithmetic) under the tail of the current one, and the
+// ~2-3 us launch gap between dependent kernels disappears.  Both are no-ops in a kernel launched without the
+// cudaLaunchAttributeProgrammaticStreamSerialization attribute (launch.h: launch_k).
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }

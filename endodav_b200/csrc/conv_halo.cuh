@@ -43,6 +43,7 @@ template <typename T, int CIN, int BN>
 __global__ void __launch_bounds__(CH_THREADS, 1)
     conv3x3_halo_kernel(const T* __restrict__ x, const T* __restrict__ w, Epi e, int F, int H, int W, int tiles_x,
                         int tiles_y, int total_tiles) {
+  pdl_launch();   // PDL: the next kernel of the stream may start its prologue (common.cuh)
   constexpr int NCH = CIN / 8;
   constexpr uint32_t W_BYTES = 9 * NCH * BN * 16;
   constexpr uint32_t HALO_BYTES = NCH * CH_PLANE;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // PDL: everything above ran under the previous kernel's tail; its results are visible from here
   const int per_frame = tiles_x * tiles_y;
   const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 

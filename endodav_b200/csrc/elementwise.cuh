@@ -12,6 +12,8 @@
 template <typename T, bool U8>
 __global__ void preprocess_patches_kernel(const void* __restrict__ src, T* __restrict__ out, int F, int H, int W,
                                           int h, int w, int Kp, int normalize) {
+  pdl_launch();
+  pdl_wait();
   // one thread = 8 consecutive k of one patch row (one aligned 16-byte store for 16-bit T)
   const int ph = h / 14, pw = w / 14;
   const int kch = Kp / 8;
@@ -124,6 +126,8 @@ __global__ void cubic_resize_u8_kernel(const uint8_t* __restrict__ src, float* _
 
 // cls row of every frame: x[f, 0, :] = cls_token + pos_embed[0]  (vision_transformer.py:225-227)
 __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ cls_row, int F, int N, int D) {
+  pdl_launch();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= F * D) return;
   int f = i / D, d = i - f * D;
@@ -141,6 +145,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, TOut* __restrict__ out,
                                                         long long Mout, int D, float eps, int grp, int skip,
                                                         const float* __restrict__ add, int add_div, int add_mod) {
+  pdl_launch();
+  pdl_wait();
   // one warp normalises TWO consecutive rows: both rows' loads are in flight before the first
   // reduction (the kernel is pure streaming: fp32 in, 16-bit out)
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -223,6 +229,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void groupnorm_stats_kernel(const T* __restrict__ x, float2* __restrict__ stats, int hw, int C, float eps) {
+  pdl_launch();
+  pdl_wait();
   const int f = blockIdx.y, g = blockIdx.x;
   const int cpg = C / 32;
   const T* base = x + (long long)f * hw * C + g * cpg;
@@ -268,6 +276,8 @@ __global__ void groupnorm_stats_kernel(const T* __restrict__ x, float2* __restri
 // values of O(1): the E[x^2]-E[x]^2 form is far inside 16-bit accuracy.
 template <typename T>
 __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const T* __restrict__ x, float2* __restrict__ part, int hw, int C) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float cs[2][2048];                // [sum|sq][pixel lane][channel], per_px * C <= 2048
   const int f = blockIdx.x;
   const int c8n = C / 8;                       // 16-byte chunks per pixel
@@ -302,6 +312,8 @@ __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const T* __restr
 // partial (sum, sumsq) over the splits (fixed order) -> (mean, rstd) in stats[f*32+g]
 __global__ void groupnorm_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int n, int nsplit,
                                           float count, float eps) {
+  pdl_launch();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int f = i >> 5, g = i & 31;
@@ -320,6 +332,8 @@ template <typename T>
 __global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __restrict__ stats,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        T* __restrict__ y, long long total8, int hw, int C) {
+  pdl_launch();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   long long e0 = i * 8;
@@ -346,6 +360,8 @@ __global__ void groupnorm_apply_kernel(const T* __restrict__ x, const float2* __
 template <typename T>
 __global__ void upsample_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y, int F, int h, int w, int oh, int ow,
                                      int C) {
+  pdl_launch();
+  pdl_wait();
   const int c8 = C / 8;
   const int j = blockIdx.y * blockDim.x + threadIdx.x;      // chunk within the output row
   if (j >= ow * c8) return;
@@ -374,6 +390,8 @@ __global__ void upsample_nhwc_kernel(const T* __restrict__ x, T* __restrict__ y,
 // (dpt_pyramid.py:95-97) and the final per-window resize (endodav.py:205).
 __global__ void resize_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int F, int h, int w, int oh,
                                   int ow, int sigmoid) {
+  pdl_launch();
+  pdl_wait();
   const long long total = (long long)F * oh * ow;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -404,6 +422,8 @@ __global__ void sigmoid_inplace_kernel(float* __restrict__ x, long long n) {
 template <typename T>
 __global__ void im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ out, int F, int H, int W, int C, int OH,
                                  int OW, int stride) {
+  pdl_launch();
+  pdl_wait();
   const int c8 = C / 8;
   const long long total = (long long)F * OH * OW * 9 * c8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -94,6 +94,24 @@ struct edv_ctx {
   unsigned long long graph_clock = 0;
   std::vector<GraphEntry> graphs;
   std::vector<GraphEntry> seen;        // pointer sets met once (no graph yet): a set is captured the SECOND time it comes by
+  // Independent decoder branches (the three shallow reassemble paths + their temporal module) run on a low-priority
+  // side stream, forked / joined with events, beside the deep path that is the critical chain (EDV_BRANCH=0: serial)
+  int branch_mode = 1;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool ensure_side() {
+    if (side_stream) return true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      branch_mode = 0;
+      return false;
+    }
+    return true;
+  }
   cudaStream_t cap_stream = nullptr;   // private capture stream: the caller's stream may be the legacy default stream, which cannot be captured
   std::string graph_note = "no capture attempted";   // why the last capture attempt did not produce a graph (edv_graph_status)
   void drop_graphs() {
@@ -106,6 +124,9 @@ struct edv_ctx {
   ~edv_ctx() {
     drop_graphs();
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (side_stream) cudaStreamDestroy(side_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
   }
   Profiler prof;
   struct Agg {
@@ -126,13 +147,30 @@ struct Fwd {
   unsigned char* ws;
   int dt, eng;
   size_t es;  // element size of the activation dtype
+  cudaStream_t main_s;
+  bool par;   // fork the independent decoder branches onto ctx->side_stream (never while profiling / tapping: both assume one serial stream)
 
-  Fwd(edv_ctx* ctx, void* workspace, cudaStream_t s) : c(ctx), ws((unsigned char*)workspace) {
+  Fwd(edv_ctx* ctx, void* workspace, cudaStream_t s) : c(ctx), ws((unsigned char*)workspace), main_s(s) {
     L.stream = s;
     L.prof = &ctx->prof;
     dt = ctx->cfg.dtype;
     eng = ctx->cfg.dtype == EDV_F32 ? EDV_ENGINE_SIMT : ctx->cfg.engine;
     es = dtype_size(dt);
+    par = ctx->branch_mode && !ctx->prof.on && !ctx->debug && ctx->ensure_side();
+  }
+  // fork: the side stream starts after everything launched on the main stream so far; join: the main stream waits for it
+  void fork_side() {
+    if (!par || !L.ok()) return;
+    if (cudaEventRecord(c->ev_fork, main_s) != cudaSuccess || cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0) != cudaSuccess)
+      return L.fail(EDV_ERR_CUDA, std::string("fork onto the side stream: ") + cudaGetErrorString(cudaGetLastError()));
+    L.stream = c->side_stream;
+  }
+  void back_to_main() { L.stream = main_s; }
+  void join_side() {
+    if (!par) return;
+    L.stream = main_s;
+    if (cudaEventRecord(c->ev_join, c->side_stream) != cudaSuccess || cudaStreamWaitEvent(main_s, c->ev_join, 0) != cudaSuccess)
+      L.fail(EDV_ERR_CUDA, std::string("join of the side stream: ") + cudaGetErrorString(cudaGetLastError()));
   }
   bool tc() const { return eng == EDV_ENGINE_TC; }
 
@@ -214,19 +252,20 @@ struct Fwd {
   }
 
   // TemporalModule (motion_module.py:60-65,102-126,164-177): X [BT*hw, C] NHWC -> Y same
-  void motion(int j, const void* X, void* Y) {
+  // `set`: scratch buffer family ("mm." on the main stream, "mmb." for the module that runs beside it on the side stream)
+  void motion(int j, const void* X, void* Y, const std::string& set = "mm.") {
     const Plan& p = c->plan;
     const int C = p.mm[j].C, hw = p.mm[j].h * p.mm[j].w, T = p.T, B = p.B;
     const long long Mm = (long long)p.BT * hw;
     const std::string n = "mm" + std::to_string(j) + ".";
-    void* gnb = buf("mm.gn");
-    float* hs = (float*)buf("mm.hs");
-    void* lnb = buf("mm.ln");
-    void* qkvb = buf("mm.qkv");
-    void* att = buf("mm.att");
-    void* gg = buf("mm.gg");
-    void* hsT = buf("mm.hsT");
-    groupnorm(L, dt, X, wf(n + "gn.w", C), wf(n + "gn.b", C), gnb, (float2*)buf("mm.stats"), p.BT, hw, C, 1e-6f);
+    void* gnb = buf((set + "gn").c_str());
+    float* hs = (float*)buf((set + "hs").c_str());
+    void* lnb = buf((set + "ln").c_str());
+    void* qkvb = buf((set + "qkv").c_str());
+    void* att = buf((set + "att").c_str());
+    void* gg = buf((set + "gg").c_str());
+    void* hsT = buf((set + "hsT").c_str());
+    groupnorm(L, dt, X, wf(n + "gn.w", C), wf(n + "gn.b", C), gnb, (float2*)buf((set + "stats").c_str()), p.BT, hw, C, 1e-6f);
     {
       Epi e = ep(hs, C, wf(n + "pin.b", C));
       e.out_f32 = 1;
@@ -251,7 +290,7 @@ struct Fwd {
       e.act = ACT_GEGLU;
       linear(lnb, Mm, C, n + "geglu.w", 8 * C, e);
     } else {
-      void* tmp = buf("mm.gg2");
+      void* tmp = buf((set + "gg2").c_str());
       linear(lnb, Mm, C, n + "geglu.w", 8 * C, ep(tmp, 8 * C, wf(n + "geglu.b", 8 * C)));
       if (L.ok()) {
         long long tot = Mm * 4 * C;
@@ -371,7 +410,7 @@ struct Fwd {
       L.check("preprocess");
       const float* cls = wf("cls_row", D);
       if (L.ok()) {
-        cls_row_kernel<<<nblk((long long)p.BT * D, 256), 256, 0, L.stream>>>(x, cls, p.BT, p.N, D);
+        edv::launch_k(cls_row_kernel, dim3(nblk((long long)p.BT * D, 256)), dim3(256), 0, L.stream, x, cls, p.BT, p.N, D);
         L.check("cls_row");
       }
       Epi e = ep(x, D, nullptr);
@@ -449,6 +488,17 @@ struct Fwd {
     void* L3 = buf("L3");
     void* L4p = buf("L4p");
     void* L4 = buf("L4");
+    // endodac (models/endodac/endodac.py:93-127) is this head without the four temporal modules
+    const bool mm_on = !g.no_motion;
+    void* L3m = mm_on ? buf("L3m") : L3;
+    void* L4m = mm_on ? buf("L4m") : L4;
+    void *l1r = buf("l1r"), *l2r = buf("l2r"), *l3r = buf("l3r"), *l4r = buf("l4r");
+    void *l1rr = buf("l1rr"), *l2rr = buf("l2rr"), *l3rr = buf("l3rr"), *l4rr = buf("l4rr");
+    // The decoder is a DAG: paths 1-3 (reassemble -> [temporal module 0] -> layer_rn) only meet the deep path at
+    // their fusion blocks.  The deep path (path 4 -> refinenet4 -> module 2 -> refinenet3 -> module 3 -> ...) is a
+    // chain of small, latency-bound launches on 19 x 19 / 37 x 37 maps that leaves most SMs idle, so paths 1-3 run
+    // beside it on the side stream (same kernels, same buffers per tensor: bit-identical to the serial order).
+    fork_side();
     {
       // projects[0] (1x1) merged with resize_layers[0] (ConvT k4 s4): one GEMM + pixel shuffle
       Epi e = ep(L1, p.Cp[0], wf("proj0.b", 16 * p.Cp[0]));
@@ -461,6 +511,17 @@ struct Fwd {
       linear(buf("tap1"), p.Mp, D, "proj1.w", 4 * p.Cp[1], e);
     }
     linear(buf("tap2"), p.Mp, D, "proj2.w", p.Cp[2], ep(L3, p.Cp[2], wf("proj2.b", p.Cp[2])));
+    if (mm_on) motion(0, L3, L3m, par ? "mmb." : "mm.");
+    // scratch.layer{1-4}_rn (3x3, no bias) -> F channels, plus relu copies for the RCUs
+    {
+      Epi e = ep(l3r, F_, nullptr); e.out_relu = l3rr;
+      conv3(L3m, p.BT, p.ph, p.pw, p.Cp[2], "rn3.w", F_, e);
+      e = ep(l2r, F_, nullptr); e.out_relu = l2rr;
+      conv3(L2, p.BT, 2 * p.ph, 2 * p.pw, p.Cp[1], "rn2.w", F_, e);
+      e = ep(l1r, F_, nullptr); e.out_relu = l1rr;
+      conv3(L1, p.BT, 4 * p.ph, 4 * p.pw, p.Cp[0], "rn1.w", F_, e);
+    }
+    back_to_main();
     linear(buf("tap3"), p.Mp, D, "proj3.w", p.Cp[3], ep(L4p, p.Cp[3], wf("proj3.b", p.Cp[3])));
     {
       // resize_layers[3]: 3x3 stride 2 pad 1 (dpt.py:85-90) = explicit im2col + GEMM
@@ -469,7 +530,7 @@ struct Fwd {
         void* col = buf("col");
         if (L.ok()) {
           long long tot = Mo * 9 * (p.Cp[3] / 8);
-          EDV_DISPATCH_T(dt, { im2col3x3_kernel<T><<<nblk(tot, 256), 256, 0, L.stream>>>((const T*)L4p, (T*)col, p.BT, p.ph, p.pw, p.Cp[3], p.ph2, p.pw2, 2); });
+          EDV_DISPATCH_T(dt, { edv::launch_k(im2col3x3_kernel<T>, dim3(nblk(tot, 256)), dim3(256), 0, L.stream, (const T*)L4p, (T*)col, p.BT, p.ph, p.pw, p.Cp[3], p.ph2, p.pw2, 2); });
           L.check("im2col");
         }
         linear(col, Mo, 9 * p.Cp[3], "resize3.w", p.Cp[3], ep(L4, p.Cp[3], wf("resize3.b", p.Cp[3])));
@@ -481,38 +542,23 @@ struct Fwd {
         if (L.ok()) gemm(L, dt, eng, a);
       }
     }
+    if (mm_on) motion(1, L4, L4m);
+    {
+      Epi e = ep(l4r, F_, nullptr); e.out_relu = l4rr;
+      conv3(L4m, p.BT, p.ph2, p.pw2, p.Cp[3], "rn4.w", F_, e);
+    }
     snapshot("layer1", L1, false, (long long)p.BT * 16 * p.P, p.Cp[0], g.out_channels[0]);
     snapshot("layer2", L2, false, (long long)p.BT * 4 * p.P, p.Cp[1], g.out_channels[1]);
     snapshot("layer3", L3, false, p.Mp, p.Cp[2], g.out_channels[2]);
     snapshot("layer4", L4, false, (long long)p.BT * p.ph2 * p.pw2, p.Cp[3], g.out_channels[3]);
-    // endodac (models/endodac/endodac.py:93-127) is this head without the four temporal modules
-    const bool mm_on = !g.no_motion;
-    void* L3m = mm_on ? buf("L3m") : L3;
-    void* L4m = mm_on ? buf("L4m") : L4;
-    if (mm_on) {
-      motion(0, L3, L3m);
-      motion(1, L4, L4m);
-    }
     snapshot("mm0", L3m, false, p.Mp, p.Cp[2], g.out_channels[2]);
     snapshot("mm1", L4m, false, (long long)p.BT * p.ph2 * p.pw2, p.Cp[3], g.out_channels[3]);
-    // scratch.layer{1-4}_rn (3x3, no bias) -> F channels, plus relu copies for the RCUs
-    void *l1r = buf("l1r"), *l2r = buf("l2r"), *l3r = buf("l3r"), *l4r = buf("l4r");
-    void *l1rr = buf("l1rr"), *l2rr = buf("l2rr"), *l3rr = buf("l3rr"), *l4rr = buf("l4rr");
-    {
-      Epi e = ep(l1r, F_, nullptr); e.out_relu = l1rr;
-      conv3(L1, p.BT, 4 * p.ph, 4 * p.pw, p.Cp[0], "rn1.w", F_, e);
-      e = ep(l2r, F_, nullptr); e.out_relu = l2rr;
-      conv3(L2, p.BT, 2 * p.ph, 2 * p.pw, p.Cp[1], "rn2.w", F_, e);
-      e = ep(l3r, F_, nullptr); e.out_relu = l3rr;
-      conv3(L3m, p.BT, p.ph, p.pw, p.Cp[2], "rn3.w", F_, e);
-      e = ep(l4r, F_, nullptr); e.out_relu = l4rr;
-      conv3(L4m, p.BT, p.ph2, p.pw2, p.Cp[3], "rn4.w", F_, e);
-    }
     void *p4 = buf("p4"), *p3 = buf("p3"), *p2 = buf("p2"), *p1 = buf("p1");
     void *p4m = mm_on ? buf("p4m") : p4, *p3m = mm_on ? buf("p3m") : p3;
     fusion(4, l4r, l4rr, nullptr, nullptr, p.ph2, p.pw2, p.ph, p.pw, p4);
     snapshot("path4_pre", p4, false, p.Mp, F_, F_);
     if (mm_on) motion(2, p4, p4m);
+    join_side();   // refinenet3 is the first consumer of the side stream's layer{1,2,3}_rn maps
     fusion(3, p4m, nullptr, l3r, l3rr, p.ph, p.pw, 2 * p.ph, 2 * p.pw, p3);
     if (mm_on) motion(3, p3, p3m);
     snapshot("path3", p3m, false, (long long)p.BT * 4 * p.P, F_, F_);
@@ -624,6 +670,7 @@ int edv_create(const edv_config* cfg, edv_ctx** out) {
   edv_ctx* c = new edv_ctx();
   c->cfg = *cfg;
   if (const char* env = getenv("EDV_GRAPH")) c->graph_mode = atoi(env) != 0;
+  if (const char* env = getenv("EDV_BRANCH")) c->branch_mode = atoi(env) != 0;
   *out = c;
   return EDV_OK;
 }
@@ -749,8 +796,21 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
     add("mm.att", mmC * es);
     add("mm.gg", mm4 * es);
     add("mm.hsT", mmC * es);
+    // second scratch family for module 0, which runs on the side stream while module 1 runs on the main one
+    const size_t r0 = (size_t)p.BT * p.mm[0].h * p.mm[0].w * p.mm[0].C;
+    add("mmb.stats", (size_t)p.BT * 32 * (1 + GN_MAX_SPLIT) * sizeof(float2), 8);
+    add("mmb.gn", r0 * es);
+    add("mmb.hs", r0 * 4, 4);
+    add("mmb.ln", r0 * es);
+    add("mmb.qkv", 3 * r0 * es);
+    add("mmb.att", r0 * es);
+    add("mmb.gg", 4 * r0 * es);
+    add("mmb.hsT", r0 * es);
   }
-  if (simt && !g.no_motion) add("mm.gg2", mm8 * es);
+  if (simt && !g.no_motion) {
+    add("mm.gg2", mm8 * es);
+    add("mmb.gg2", 8 * (size_t)p.BT * p.mm[0].h * p.mm[0].w * p.mm[0].C * es);
+  }
   add("l1r", px1 * F_ * es); add("l1rr", px1 * F_ * es);
   add("l2r", px2 * F_ * es); add("l2rr", px2 * F_ * es);
   add("l3r", px3 * F_ * es); add("l3rr", px3 * F_ * es);
@@ -870,8 +930,10 @@ static int forward_common(edv_ctx* ctx, const void* frames, bool u8, float* cons
   }
   // Capture on a private stream and replay on the caller's: the capture itself executes nothing, and the caller's
   // stream is usually torch's current stream = the legacy default stream, which cudaStreamBeginCapture refuses.
-  if (!ctx->cap_stream && cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
-    ctx->graph_note = std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(cudaGetLastError());
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the captured main chain outranks the side-stream branches
+  if (!ctx->cap_stream && cudaStreamCreateWithPriority(&ctx->cap_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+    ctx->graph_note = std::string("cudaStreamCreateWithPriority: ") + cudaGetErrorString(cudaGetLastError());
     ctx->cap_stream = nullptr;
     ctx->graph_mode = 0;
     Fwd f(ctx, workspace_dev, st);

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gemm_bres_kernel(const __grid_c
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmC, Epi e, int M, int K,
                                                                   int stages, int n_tiles, int m_tiles) {
+  pdl_launch();   // PDL: the next kernel of the stream may start its prologue (common.cuh)
   constexpr uint32_t B_KB_BYTES = BN * 128;                 // one 64-wide k-block of the resident W tile
   constexpr uint32_t TMEM_COLS = gb_tmem_cols<BN>();
   constexpr int CW = BN / 4;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gemm_bres_kernel(const __grid_c
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // PDL: everything above ran under the previous kernel's tail; its results are visible from here
   if (tm_ && threadIdx.x == 0) tm_[1] = clock64();
 
   if (warp == 0) {

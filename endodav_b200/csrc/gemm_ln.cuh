@@ -81,6 +81,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GL_THREADS, 1)
                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXn, const float* __restrict__ bias,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int M, int K, int m_tiles, int do_ln,
                    long long* __restrict__ tim) {
+  pdl_launch();   // PDL: the next kernel of the stream may start its prologue (common.cuh)
   // tim: optional timeline of cluster 0's even CTA: per tile i < 8, slots [8i..8i+7] = residual loads issued, accumulator
   // complete, pass 1 done, mean known, pass 2 done, peer statistics in, pass 3 done (clock64)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -136,6 +137,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GL_THREADS, 1)
   cluster_sync_all();                       // both CTAs' barriers exist before any remote arrive
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // PDL: everything above ran under the previous kernel's tail; its results are visible from here
 
   if (warp == 0) {
     if (lane == 0) {

@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmC, Epi e, int M,
                                                                 int N, int K, int stages, ConvTile ct, int n_tiles,
                                                                 int total_tiles) {
+  pdl_launch();   // PDL: the next kernel of the stream may start its prologue (common.cuh)
   constexpr uint32_t ROW_BYTES = BK * 2;                    // 128 (BK=64) or 64 (BK=32)
   constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
   constexpr uint32_t SBO = 8 * ROW_BYTES;                   // 8-row swizzle atom
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // PDL: everything above ran under the previous kernel's tail; its results are visible from here
   if (tm_ && threadIdx.x == 0) tm_[1] = clock64();
 
   if (warp == 0) {

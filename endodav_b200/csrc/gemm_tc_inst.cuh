@@ -86,7 +86,7 @@ void launch_gemm_tc_inst(Launch& L, int dtype, const GemmArgs& a) {
   const int grid = (int)std::min<long long>(total, num_sms());
   (void)kblocks;
   note_gemm(L, a, 2);
-  kern<<<grid, GT_THREADS, smem, L.stream>>>(tmA, tmB, tmC, a2.e, a.M, a.N, a.K, stages, ct, n_tiles, (int)total);
+  edv::launch_k(kern, dim3(grid), dim3(GT_THREADS), smem, L.stream, tmA, tmB, tmC, a2.e, a.M, a.N, a.K, stages, ct, n_tiles, (int)total);
   L.check("gemm_tc");
 }
 
@@ -104,7 +104,7 @@ template <typename T, int BN> void launch_conv_halo(Launch& L, const GemmArgs& a
   if (total > 0x7fffffffLL) return L.fail(EDV_ERR_ARG, "conv_halo: too many tiles");
   const int grid = (int)std::min<long long>(total, num_sms());
   note_gemm(L, a, 2);
-  kern<<<grid, CH_THREADS, ch_smem_bytes<64, BN>(), L.stream>>>((const T*)a.A, (const T*)a.W, a.e, a.F, a.H, a.Wd, tiles_x,
+  edv::launch_k(kern, dim3(grid), dim3(CH_THREADS), ch_smem_bytes<64, BN>(), L.stream, (const T*)a.A, (const T*)a.W, a.e, a.F, a.H, a.Wd, tiles_x,
                                                                tiles_y, (int)total);
   L.check("conv_halo");
 }
@@ -246,7 +246,7 @@ template <typename T, int BN> bool launch_gemm_bres(Launch& L, int dtype, const 
   GemmArgs a2 = a;
   a2.e.kind |= EF_TMA_OUT;
   note_gemm(L, a, 2);
-  kern<<<grid, GB_THREADS, smem, L.stream>>>(tmA, tmB, tmC, a2.e, a.M, a.K, stages, n_tiles, m_tiles);
+  edv::launch_k(kern, dim3(grid), dim3(GB_THREADS), smem, L.stream, tmA, tmB, tmC, a2.e, a.M, a.K, stages, n_tiles, m_tiles);
   L.check("gemm_bres");
   return true;
 }
@@ -290,7 +290,7 @@ void launch_gemm_ln(Launch& L, int dtype, const void* A, const void* W, const fl
   const int grid = 2 * std::min(m_tiles, num_sms() / 2);   // clusters of two CTAs, one 128-row tile per pair at a time
   // algorithmic work: 2 M N K; bytes: A + W + the fp32 stream read and written once + xn written once
   L.note(2.0 * M * GL_N * K, ((double)M * K + (double)GL_N * K) * 2 + (double)M * GL_N * (8 + (do_ln ? 2 : 0)));
-  kern<<<grid, GL_THREADS, GL_SMEM, L.stream>>>(tmA, tmB, tmX, tmXn, bias, gamma, beta, eps, M, K, m_tiles, do_ln, tim);
+  edv::launch_k(kern, dim3(grid), dim3(GL_THREADS), GL_SMEM, L.stream, tmA, tmB, tmX, tmXn, bias, gamma, beta, eps, M, K, m_tiles, do_ln, tim);
   L.check("gemm_ln");
 }
 

@@ -21,7 +21,7 @@ void launch_head_fused(Launch& L, const void* x, const void* w, const float* bia
   const int grid = (int)std::min<long long>(total, num_sms());
   // algorithmic bytes: the low-resolution map once + one float per output pixel
   L.note(2.0 * F * OH * OW * 32.0 * (9 * CIN + 1), (double)F * H1 * W1 * CIN * sizeof(T) + (double)F * OH * OW * 4);
-  kern<<<grid, HF_THREADS, hf_smem_bytes<CIN>(), L.stream>>>((const T*)x, (const T*)w, bias, head_w, out, F, H1, W1, OH, OW,
+  edv::launch_k(kern, dim3(grid), dim3(HF_THREADS), hf_smem_bytes<CIN>(), L.stream, (const T*)x, (const T*)w, bias, head_w, out, F, H1, W1, OH, OW,
                                                            sig_sign, tiles_x, tiles_y, (int)total);
   L.check("head_fused");
 }

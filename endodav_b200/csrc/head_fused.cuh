@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
     head_fused_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ head_w, float* __restrict__ out, int F, int H1, int W1, int OH, int OW,
                       float sig_sign, int tiles_x, int tiles_y, int total_tiles) {
+  pdl_launch();   // PDL: the next kernel of the stream may start its prologue (common.cuh)
   constexpr int NCH = CIN / 8;                     // 16-byte channel chunks per pixel
   constexpr uint32_t W_BYTES = 9 * NCH * 512;
   constexpr uint32_t HALO_BYTES = NCH * HF_PLANE;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(HF_THREADS, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // PDL: everything above ran under the previous kernel's tail; its results are visible from here
   const int per_frame = tiles_x * tiles_y;
 
   if (warp >= 5) {

@@ -2,12 +2,38 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/endodav_b200.h"
 
 namespace edv {
+
+// EDV_PDL=0 launches every kernel fully serialised (no programmatic dependent launch)
+inline bool pdl_enabled() {
+  static const bool v = [] { const char* e = getenv("EDV_PDL"); return !e || atoi(e) != 0; }();
+  return v;
+}
+
+// kern<<<grid, block, smem, stream>>>(args...) with programmatic stream serialisation: the kernel may be scheduled
+// while its predecessor in the stream is still running and must call pdl_wait() (common.cuh) before touching global
+// memory.  Works under stream capture (programmatic edges in the captured graph).
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // Optional per-launch timing: one CUDA event after every launch on the launching stream, so
 // the duration of launch i is event[i] - event[i-1] (the stream is serial).  Used by bench.py

@@ -67,11 +67,11 @@ inline void layernorm(Launch& L, int dtype, const float* x, const float* g, cons
   const unsigned blocks = nblk(((Mout + 1) / 2) * 32, 256);   // one warp per two rows
   L.note(0, (double)Mout * D * (4 + dtype_size(dtype)));
   EDV_DISPATCH_T(dtype, {
-    if (maxv <= 1) layernorm_kernel<T, 1><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
-    else if (maxv <= 2) layernorm_kernel<T, 2><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
-    else if (maxv <= 3) layernorm_kernel<T, 3><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
-    else if (maxv <= 4) layernorm_kernel<T, 4><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
-    else layernorm_kernel<T, 8><<<blocks, 256, 0, L.stream>>>(x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    if (maxv <= 1) edv::launch_k(layernorm_kernel<T, 1>, dim3(blocks), dim3(256), 0, L.stream, x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else if (maxv <= 2) edv::launch_k(layernorm_kernel<T, 2>, dim3(blocks), dim3(256), 0, L.stream, x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else if (maxv <= 3) edv::launch_k(layernorm_kernel<T, 3>, dim3(blocks), dim3(256), 0, L.stream, x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else if (maxv <= 4) edv::launch_k(layernorm_kernel<T, 4>, dim3(blocks), dim3(256), 0, L.stream, x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
+    else edv::launch_k(layernorm_kernel<T, 8>, dim3(blocks), dim3(256), 0, L.stream, x, g, b, (T*)y, Mout, D, eps, grp, skip, add, add_div, add_mod);
   });
   L.check("layernorm");
 }
@@ -86,7 +86,7 @@ inline void groupnorm(Launch& L, int dtype, const void* x, const float* g, const
     // fp32 path: two-pass (mean, then centred variance) per (frame, group)
     EDV_DISPATCH_T(dtype, {
       L.note(0, (double)F * hw * C * sizeof(T));
-      groupnorm_stats_kernel<T><<<dim3(32, F), 256, 0, L.stream>>>((const T*)x, stats, hw, C, eps);
+      edv::launch_k(groupnorm_stats_kernel<T>, dim3(32, F), dim3(256), 0, L.stream, (const T*)x, stats, hw, C, eps);
     });
     L.check("groupnorm_stats");
   } else {
@@ -97,16 +97,16 @@ inline void groupnorm(Launch& L, int dtype, const void* x, const float* g, const
     float2* part = stats + (size_t)F * 32;                 // caller provides F*32*(1+GN_MAX_SPLIT) entries
     EDV_DISPATCH_T(dtype, {
       L.note(0, (double)F * hw * C * sizeof(T));
-      groupnorm_partial_kernel<T><<<dim3(F, split), 256, 0, L.stream>>>((const T*)x, part, hw, C);
+      edv::launch_k(groupnorm_partial_kernel<T>, dim3(F, split), dim3(256), 0, L.stream, (const T*)x, part, hw, C);
     });
     L.check("groupnorm_stats");
-    groupnorm_finalize_kernel<<<nblk((long long)F * 32, 256), 256, 0, L.stream>>>(part, stats, F * 32, split, (float)hw * (C / 32), eps);
+    edv::launch_k(groupnorm_finalize_kernel, dim3(nblk((long long)F * 32, 256)), dim3(256), 0, L.stream, part, stats, F * 32, split, (float)hw * (C / 32), eps);
     L.check("groupnorm_finalize");
   }
   EDV_DISPATCH_T(dtype, {
     long long total8 = (long long)F * hw * C / 8;
     L.note(0, 2.0 * F * hw * C * sizeof(T));
-    groupnorm_apply_kernel<T><<<nblk(total8, 256), 256, 0, L.stream>>>((const T*)x, stats, g, b, (T*)y, total8, hw, C);
+    edv::launch_k(groupnorm_apply_kernel<T>, dim3(nblk(total8, 256)), dim3(256), 0, L.stream, (const T*)x, stats, g, b, (T*)y, total8, hw, C);
   });
   L.check("groupnorm_apply");
 }
@@ -118,7 +118,7 @@ inline void upsample(Launch& L, int dtype, const void* x, void* y, int F, int h,
   if (rows > 0x7fffffffLL || per_row > 65535LL * 256) return L.fail(EDV_ERR_ARG, "upsample: map too large");
   L.note(0, ((double)F * h * w + (double)F * oh * ow) * C * dtype_size(dtype));
   const dim3 grid((unsigned)rows, (unsigned)((per_row + 255) / 256));
-  EDV_DISPATCH_T(dtype, { upsample_nhwc_kernel<T><<<grid, 256, 0, L.stream>>>((const T*)x, (T*)y, F, h, w, oh, ow, C); });
+  EDV_DISPATCH_T(dtype, { edv::launch_k(upsample_nhwc_kernel<T>, dim3(grid), dim3(256), 0, L.stream, (const T*)x, (T*)y, F, h, w, oh, ow, C); });
   L.check("upsample");
 }
 
@@ -126,7 +126,7 @@ inline void resize_f32(Launch& L, const float* x, float* y, int F, int h, int w,
   if (!L.ok()) return;
   long long total = (long long)F * oh * ow;
   L.note(0, ((double)F * h * w + (double)F * oh * ow) * 4);
-  resize_f32_kernel<<<nblk(total, 256), 256, 0, L.stream>>>(x, y, F, h, w, oh, ow, sigmoid);
+  edv::launch_k(resize_f32_kernel, dim3(nblk(total, 256)), dim3(256), 0, L.stream, x, y, F, h, w, oh, ow, sigmoid);
   L.check("resize_f32");
 }
 
