@@ -257,8 +257,8 @@ def temporal_module(c, x, j, B, T, unmerged=False):
 
 def _apply_rope(q, k, dim, T, theta=10000.0):
     """motion_module/attention.py:403-429 (precompute_freqs_cis / apply_rotary_emb)."""
-    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[: (dim // 2)].float() / dim))
-    t = torch.arange(T)
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2, device=q.device)[: (dim // 2)].float() / dim))
+    t = torch.arange(T, device=q.device)
     freqs = torch.outer(t, freqs).float()
     fc = torch.polar(torch.ones_like(freqs), freqs)  # [T, dim/2]
     q_ = torch.view_as_complex(q.float().reshape(*q.shape[:-1], -1, 2))
@@ -371,8 +371,8 @@ def forward(sd, x, cfg=None, image_shape=(224, 280), emulate_bf16=False, unmerge
     c = _Ctx(sd, cfg, emulate_bf16, record)
     B, T = x.shape[:2]
     xr = F.interpolate(x.flatten(0, 1).float(), size=tuple(image_shape), mode="bilinear", align_corners=True)
-    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    mean = torch.tensor(IMAGENET_MEAN, device=xr.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, device=xr.device).view(1, 3, 1, 1)
     xn = (xr - mean) / std
     ph, pw = xn.shape[-2] // 14, xn.shape[-1] // 14
     taps = encoder_taps(c, xn, unmerged)
@@ -396,7 +396,7 @@ def forward_endodac(sd, x, cfg, image_shape=(224, 280), pre_norm=False, inv_sigm
         x = x.flatten(0, 1)
     xr = F.interpolate(x.float(), size=tuple(image_shape), mode="bilinear", align_corners=True)
     if pre_norm:
-        xr = (xr - torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)) / torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+        xr = (xr - torch.tensor(IMAGENET_MEAN, device=xr.device).view(1, 3, 1, 1)) / torch.tensor(IMAGENET_STD, device=xr.device).view(1, 3, 1, 1)
     ph, pw = xr.shape[-2] // 14, xr.shape[-1] // 14
     taps = encoder_taps(c, xr, unmerged)
     return dpt_head(c, taps, ph, pw, 1, unmerged, inv_sigmoid, False)
