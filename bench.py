@@ -232,6 +232,7 @@ def time_video_config3(E, synthetic, dev, world, rank, dist, n_frames=2000):
     import torch
 
     ctor, _ = WORKLOADS["vits_224x280_t32"]
+    torch.manual_seed(0)   # the base init draws from the global RNG: every rank must build the same weights
     model = E.endodav(dtype="fp16", **ctor)
     synthetic.randomize_(model, 1234)
     model = model.to(dev).eval()
@@ -260,6 +261,7 @@ def time_video_config3(E, synthetic, dev, world, rank, dist, n_frames=2000):
                scaling="strong", n_gpus=world)
     if world > 1:
         if rank == 0:
+            run(False)                # warm-up of the single-GPU schedule (its own plan / graphs / pinned ring)
             single, s1 = run(False)
             res["bitwise_equal_to_1gpu"] = bool(np.array_equal(out, single))
             res["seconds_1gpu_same_process"] = s1
