@@ -114,10 +114,10 @@ inline void groupnorm(Launch& L, int dtype, const void* x, const float* g, const
 inline void upsample(Launch& L, int dtype, const void* x, void* y, int F, int h, int w, int oh, int ow, int C) {
   if (!L.ok()) return;
   if (C % 8 != 0) return L.fail(EDV_ERR_ARG, "upsample: C must be a multiple of 8");
-  const long long rows = (long long)F * oh, per_row = (long long)ow * (C / 8);
-  if (rows > 0x7fffffffLL || per_row > 65535LL * 256) return L.fail(EDV_ERR_ARG, "upsample: map too large");
+  const long long bands = (long long)F * ((oh + UP_ROWS - 1) / UP_ROWS), per_row = (long long)ow * (C / 8);
+  if (bands > 0x7fffffffLL || per_row > 65535LL * 256) return L.fail(EDV_ERR_ARG, "upsample: map too large");
   L.note(0, ((double)F * h * w + (double)F * oh * ow) * C * dtype_size(dtype));
-  const dim3 grid((unsigned)rows, (unsigned)((per_row + 255) / 256));
+  const dim3 grid((unsigned)bands, (unsigned)((per_row + 255) / 256));
   EDV_DISPATCH_T(dtype, { edv::launch_k(upsample_nhwc_kernel<T>, dim3(grid), dim3(256), 0, L.stream, (const T*)x, (T*)y, F, h, w, oh, ow, C); });
   L.check("upsample");
 }
