@@ -224,6 +224,46 @@ def time_forward(E, synthetic, workload, dtype, dev, steps, warmup):
     return out
 
 
+def time_config5_sweep(E, synthetic, dtype, dev):
+    """BASELINE config 5 (Hamlyn-shaped clip-batch sweep at 256x320, network resolution 224x280), a bounded subset of
+    tools/sweep_clips.py: frames/s of endodav.forward and the temporal-attention kernel's share / bandwidth."""
+    import torch
+
+    ctor, _ = WORKLOADS["vits_224x280_t32"]
+    model = E.endodav(dtype=dtype, **ctor)
+    synthetic.randomize_(model, 1234)
+    model = model.to(dev).eval()
+    rows = []
+    for T in (8, 32):
+        for B in (1, 8, 64):
+            x = torch.rand(B, T, 3, 256, 320, device=dev)
+            for _ in range(3):
+                model(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10 if B * T <= 512 else 3
+            e0.record()
+            for _ in range(reps):
+                model(x)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            eng = model._eng
+            eng.profile(True)
+            model(x)
+            tab = eng.profile_collect()
+            eng.profile(False)
+            tot = sum(r["ms"] for r in tab) or 1.0
+            ta = sum(r["ms"] for r in tab if r["name"].startswith("temporal_attention"))
+            tb = sum(r["bytes"] for r in tab if r["name"].startswith("temporal_attention"))
+            rows.append(dict(clips=B, T=T, ms=ms, frames_per_s=B * T / ms * 1e3, temporal_attention_share=ta / tot,
+                             temporal_attention_gbs=tb / (ta * 1e-3) / 1e9 if ta else 0.0))
+            del x
+    del model
+    torch.cuda.empty_cache()
+    return dict(frame=[256, 320], network_resolution=[224, 280], dtype=dtype, rows=rows)
+
+
 def time_video_config3(E, synthetic, dev, world, rank, dist, n_frames=2000):
     """BASELINE config 3: SCARED-shaped 2 000-frame 256x320 video through infer_video_depth, windows sharded over the
     ranks (strong scaling: the video is fixed).  Host uint8 frames in, host float32 depth out; wall clock between
@@ -445,6 +485,12 @@ def main():
             if world == 1:
                 extra["config1_vits_224x280_t8"] = time_forward(E, synthetic, "vits_224x280_t8", args.dtype, dev, 50, 10)
                 extra["vits_224x280_t32"] = time_forward(E, synthetic, "vits_224x280_t32", args.dtype, dev, 50, 10)
+                for name, fn in (("config4_vitl_518_t32_b4", lambda: time_forward(E, synthetic, "vitl_518_t32_b4", args.dtype, dev, 3, 3)),
+                                 ("config5_sweep", lambda: time_config5_sweep(E, synthetic, args.dtype, dev))):
+                    try:
+                        extra[name] = fn()
+                    except Exception as exc:  # the headline line must survive a failure of an extra
+                        extra[name] = dict(error=repr(exc)[:300])
         if world > 1:
             dist.barrier()
         try:
