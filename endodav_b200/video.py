@@ -15,6 +15,7 @@ per-window disparity to rank 0 (``torch.distributed``); there is no collective i
 network.  With torch.distributed not initialised this is the single-GPU path.
 """
 import os
+import time
 
 import numpy as np
 import torch
@@ -135,6 +136,70 @@ class _FrameCache:
             t = np.ascontiguousarray(np.transpose(img, (2, 0, 1))).astype(np.float32)
             self.cache[idx] = t
         return t
+
+
+class _Stager:
+    """Host-side staging of the raw uint8 frames of window batches into pinned memory, off the launching thread.
+
+    A batch is WB windows x 32 frames; window k > 0 is two single frames plus ONE contiguous run of 30 frames
+    (``window_frame_indices``), so staging is three bulk copies per window.  Done inline it costs 10-17 ms per batch of four
+    256x320 windows when eight ranks stage at once -- more than the 9.5 ms the GPU needs for that batch, and the first
+    batch delayed every rank's first kernel (measured with ENDODAV_TRACE=1: the 8-GPU long-video run was bound by exactly
+    this).  Here every window of a batch is copied by its own worker thread (torch's copy releases the GIL), and the
+    next two batches of the caller's (sequential) schedule are staged while the current one is uploaded and computed.
+    Ring of three pinned buffers; a buffer is rewritten only after the H2D copy that read it has completed."""
+
+    RING = 3
+
+    def __init__(self, frames, n_frames, mine, WB, H, W):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.frames, self.n, self.mine, self.WB = frames, n_frames, mine, WB
+        self.bufs = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8, pin_memory=True) for _ in range(self.RING)]
+        self.h2d_done = [None] * self.RING
+        self.pool = ThreadPoolExecutor(max_workers=max(1, min(4, WB)))
+        import weakref
+        weakref.finalize(self, self.pool.shutdown, False)   # the worker threads go away with the stager
+        self.tasks = {}          # (j, nb) -> (slot, futures)
+        self.count = 0
+
+    def _fill(self, slot, b, k, ev):
+        if ev is not None:
+            ev.synchronize()     # the earlier upload out of this buffer has finished
+        dst = self.bufs[slot][b * INFER_LEN:(b + 1) * INFER_LEN]
+        idx = window_frame_indices(k, self.n)
+        if int(idx[-1]) - int(idx[2]) == INFER_LEN - 3:
+            dst[2:].copy_(torch.from_numpy(self.frames[int(idx[2]): int(idx[-1]) + 1]))
+            dst[0].copy_(torch.from_numpy(self.frames[int(idx[0])]))
+            dst[1].copy_(torch.from_numpy(self.frames[int(idx[1])]))
+        else:                    # the clamped tail of the video: frame by frame
+            np.take(self.frames, idx, axis=0, out=dst.numpy())
+
+    def submit(self, j, nb):
+        if nb <= 0 or j >= len(self.mine) or (j, nb) in self.tasks:
+            return
+        slot = self.count % self.RING
+        self.count += 1
+        ev, self.h2d_done[slot] = self.h2d_done[slot], None
+        self.tasks[(j, nb)] = (slot, [self.pool.submit(self._fill, slot, b, self.mine[j + b], ev) for b in range(nb)])
+
+    def fetch(self, j, nb):
+        """-> (slot, pinned uint8 [nb*32,H,W,3]) for windows mine[j:j+nb]; stages the next two batches of a sequential
+        schedule in the background."""
+        self.submit(j, nb)
+        slot, futs = self.tasks.pop((j, nb))
+        for ahead in (1, 2):
+            jn = j + ahead * nb
+            self.submit(jn, min(nb, len(self.mine) - jn))
+        for f in futs:
+            f.result()
+        return slot, self.bufs[slot][: nb * INFER_LEN]
+
+    def uploaded(self, slot, event):
+        self.h2d_done[slot] = event
+
+    def close(self):
+        self.pool.shutdown(wait=True)
 
 
 def final_frame_range(k, n_windows, n_frames):
@@ -264,10 +329,12 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
         # 2000 frames), fewer at larger network resolutions (the workspace grows with WB*32 frames)
         wb_default = max(1, min(4, int(round(4.0 * 224 * 280 / (new_h * new_w)))))
         WB = max(1, int(os.environ.get("ENDODAV_WINDOW_BATCH", wb_default))) if (gpu_stitch or world > 1) else 1
+        stager = None
         if gpu_pre:
             # the staging buffers hold raw frames: bound them by the FRAME size too (256 MB each; 1080p -> one window)
             WB = max(1, min(WB, (256 << 20) // (INFER_LEN * H * W * 3)))
-            pinned = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+            stager = _Stager(frames, n, mine, WB, H, W)
+            pinned = None
         else:
             pinned = [torch.empty(WB, INFER_LEN, 3, new_h, new_w, dtype=torch.float32, pin_memory=True) for _ in range(2)]
         copied = [None, None]
@@ -284,25 +351,27 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
             device tensor [nb*32,H,W]"""
             slot = calls[0] & 1
             calls[0] += 1
-            if copied[slot] is not None:
-                copied[slot].synchronize()  # the earlier H2D copy out of this buffer has finished
-            buf = pinned[slot]
-            idx = np.concatenate([window_frame_indices(mine[j + b], n) for b in range(nb)])
             x = dev_x[slot][: nb * INFER_LEN]
             if gpu_pre:
-                np.take(frames, idx, axis=0, out=buf.numpy()[: nb * INFER_LEN])
+                pslot, buf = stager.fetch(j, nb)
                 xu8 = dev_u8[slot][: nb * INFER_LEN]
-                xu8.copy_(buf[: nb * INFER_LEN], non_blocking=True)
+                xu8.copy_(buf, non_blocking=True)
             else:
+                if copied[slot] is not None:
+                    copied[slot].synchronize()  # the earlier H2D copy out of this buffer has finished
+                buf = pinned[slot]
+                idx = np.concatenate([window_frame_indices(mine[j + b], n) for b in range(nb)])
                 flat = buf.view(WB * INFER_LEN, 3, new_h, new_w)
                 for i, src in enumerate(idx):
                     flat[i].copy_(torch.from_numpy(cache.get(int(src))))
                 x.copy_(flat[: nb * INFER_LEN], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-            copied[slot] = ev
             if gpu_pre:
+                stager.uploaded(pslot, ev)
                 _engine.op_cubic_resize_u8(xu8, new_h, new_w, out=x)
+            else:
+                copied[slot] = ev
             if out is None:
                 if dev_out[slot] is None:
                     dev_out[slot] = torch.empty(WB * INFER_LEN, H, W, dtype=torch.float32, device=dev)
@@ -383,6 +452,13 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                         consumed[r % POOL].record(side)
 
                 prev = None
+                trace = [] if os.environ.get("ENDODAV_TRACE") else None     # host-side timeline of the rounds (ms since entry)
+                t_entry = time.perf_counter()
+
+                def mark(what):
+                    if trace is not None:
+                        trace.append("%s@%.1f" % (what, 1e3 * (time.perf_counter() - t_entry)))
+
                 for r, j0 in enumerate(range(0, per, WB)):
                     nb = min(WB, per - j0)
                     have = max(0, min(nb, len(mine) - j0))             # real windows of this rank in the round
@@ -391,27 +467,39 @@ def infer_video_depth(model, frames, device="cuda", forward_window=None, distrib
                     if rank == 0 and consumed[r % POOL] is not None:
                         torch.cuda.current_stream().wait_event(consumed[r % POOL])
                     send = sends[r % POOL][:nb]
+                    mark("r%d:ready" % r)
                     if have:
                         launch(j0, have, send[:have].view(have * INFER_LEN, H, W))
+                    mark("launched")
                     if have < nb:
                         send[have:].zero_()
                     bufs = [t[:nb] for t in recvs[r % POOL]] if rank == 0 else None
                     work = dist.gather(send, bufs, dst=0, async_op=True)
                     works[r % POOL] = work
+                    mark("gather")
                     if rank == 0:
                         if prev is not None:
                             consume(*prev)
                         prev = (r, j0, nb, bufs, work)
+                        mark("consumed")
                 if rank == 0:
                     consume(*prev)
+                    mark("last-consume")
                     with torch.cuda.stream(side):
                         result = st.finish()
+                    mark("finish")
                     torch.cuda.current_stream().synchronize()
+                    mark("sync")
+                    if trace is not None:
+                        print("[endodav trace rank 0] " + " ".join(trace), flush=True)
                     return result
                 for work in works:
                     if work is not None:
                         work.wait()
                 torch.cuda.current_stream().synchronize()
+                mark("sync")
+                if trace is not None and rank in (1, world - 1):
+                    print("[endodav trace rank %d] " % rank + " ".join(trace), flush=True)
                 return None
         # ENDODAV_GATHER=single: every window's disparity is written straight into this rank's (padded) slice of
         # ONE gather issued after the last window

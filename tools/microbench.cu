@@ -28,7 +28,7 @@ using namespace tc;
 // One CTA: thread 32 issues `groups` x 4 MMAs (K = 16 each; 4 = one 64-wide k-block), commits, waits.
 // TS: A operand from TMEM (as P in the attention kernel).  BMN: B stored MN-major (as V).
 // ALT: alternate between two accumulators (independent chains) instead of one.
-template <int N, bool TS, bool BMN, bool ALT>
+template <int N, bool TS, bool BMN, bool ALT, int MM = 128>
 __global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int groups) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench(long long* out, int groups) 
   fence_after_sync();
   const uint32_t tm = *slot;
   if (threadIdx.x == 32) {
-    constexpr uint32_t idesc = make_idesc<f16>(128, N, BMN ? 1 : 0);
+    constexpr uint32_t idesc = make_idesc<f16>(MM, N, BMN ? 1 : 0);
     const uint64_t adesc = make_smem_desc(smem_u32(sA), 1024, 16, SWZ_128B);
     const uint64_t bdesc = BMN ? make_smem_desc(smem_u32(sB), 1024, 1024, SWZ_128B) : make_smem_desc(smem_u32(sB), 1024, 16, SWZ_128B);
     // warm-up
@@ -306,6 +306,21 @@ template <int N, bool TS, bool BMN, bool ALT> void run_mma_u(const char* what, l
          128.0 * N * 16 / per);
 }
 
+// M = 64 instructions (the "weights as A, pixels as B" formulation of the 64-channel convolutions)
+template <int N, int MM> void run_mma_m(const char* what, long long* d_out, int nblocks) {
+  const int groups = 512;
+  auto kern = mma_bench<N, false, false, false, MM>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 16384 + 32768 + 64));
+  kern<<<nblocks, 128, 1024 + 16384 + 32768 + 64>>>(d_out, groups);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(nblocks);
+  CK(cudaMemcpy(h.data(), d_out, nblocks * sizeof(long long), cudaMemcpyDeviceToHost));
+  double s = 0;
+  for (long long v : h) s += (double)v;
+  const double per = s / nblocks / (groups * 4);
+  printf("mma %-26s M=%3d N=%3d ctas=%3d: %7.1f cycles / MMA (K=16)  -> %6.0f MAC/cycle/SM\n", what, MM, N, nblocks, per, (double)MM * N * 16 / per);
+}
+
 template <int N, bool TS, bool BMN, bool ALT> void run_mma(const char* what, long long* d_out, int nblocks) {
   auto kern = mma_bench<N, TS, BMN, ALT>;
   const int smem = 1024 + 16384 + 32768 + 64;
@@ -507,6 +522,19 @@ int main(int argc, char** argv) {
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   printf("SMs: %d\n", sms);
+  if (argc > 1 && std::string(argv[1]) == "m64") {
+    for (int nb : {1, sms}) {
+      run_mma_m<32, 64>("SS K-major", d_out, nb);
+      run_mma_m<64, 64>("SS K-major", d_out, nb);
+      run_mma_m<128, 64>("SS K-major", d_out, nb);
+      run_mma_m<256, 64>("SS K-major", d_out, nb);
+      run_mma_m<64, 128>("SS K-major", d_out, nb);
+      run_mma_m<128, 128>("SS K-major", d_out, nb);
+      run_mma_m<256, 128>("SS K-major", d_out, nb);
+    }
+    printf("done\n");
+    return 0;
+  }
   if (only_mix) {
     run_mix_all(d_f, d_out);
     printf("done\n");
