@@ -527,7 +527,7 @@ __global__ void rowln_act_kernel(const T* __restrict__ x, const float* __restric
 // x[f, 1+p, :] += LN_cf(r[f*P+p, :])   -- the residual-block add into patch tokens (block.py:146-150)
 template <typename T>
 __global__ void resblock_add_kernel(float* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, long long Mp, int P, int D, float eps) {
+                                    const float* __restrict__ beta, long long Mp, int P, int D, float eps, int cls) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= Mp) return;
@@ -538,20 +538,20 @@ __global__ void resblock_add_kernel(float* __restrict__ x, const T* __restrict__
   float q = 0.f;
   for (int c = lane; c < D; c += 32) { float d = to_f<T>(rr[c]) - mean; q += d * d; }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
-  float* xr = x + (warp + warp / P + 1) * D;
+  float* xr = x + (cls ? warp + warp / P + 1 : warp) * D;   // cls: skip the frame's cls row
   for (int c = lane; c < D; c += 32)
     xr[c] += (to_f<T>(rr[c]) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
 }
 
 // compact copy of the patch tokens of the fp32 residual stream into T (drops cls rows)
 template <typename T>
-__global__ void tokens_to_patches_kernel(const float* __restrict__ x, T* __restrict__ y, long long Mp, int P, int D) {
+__global__ void tokens_to_patches_kernel(const float* __restrict__ x, T* __restrict__ y, long long Mp, int P, int D, int cls) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = Mp * (D / 4);
   if (i >= total) return;
   long long r = i / (D / 4);
   int c = (int)(i - r * (D / 4)) * 4;
   float v[4];
-  load_vec<float, 4>(x + (r + r / P + 1) * D + c, v);
+  load_vec<float, 4>(x + (cls ? r + r / P + 1 : r) * D + c, v);
   store_vec<T, 4>(y + r * D + c, v);
 }

@@ -408,13 +408,13 @@ struct Fwd {
         else preprocess_patches_kernel<T, false><<<blocks, 256, 0, L.stream>>>(frames, (T*)A0, p.BT, p.H, p.W, p.h, p.w, KPATCH, nrm);
       });
       L.check("preprocess");
-      const float* cls = wf("cls_row", D);
-      if (L.ok()) {
+      const float* cls = g.no_cls ? nullptr : wf("cls_row", D);
+      if (cls && L.ok()) {
         edv::launch_k(cls_row_kernel, dim3(nblk((long long)p.BT * D, 256)), dim3(256), 0, L.stream, x, cls, p.BT, p.N, D);
         L.check("cls_row");
       }
       Epi e = ep(x, D, nullptr);
-      e.out_f32 = 1; e.map = MAP_TOKENS; e.map_p = p.P;
+      e.out_f32 = 1; e.map = g.no_cls ? MAP_LINEAR : MAP_TOKENS; e.map_p = p.P;   // no cls token: token row = patch row
       e.rowbias = wf("patch.pos", (size_t)p.P * D);
       e.rb_div = 1; e.rb_mod = p.P; e.rb_ld = D;
       linear(A0, p.Mp, KPATCH, "patch.w", D, e);
@@ -475,7 +475,7 @@ struct Fwd {
         char tn[16];
         snprintf(tn, sizeof tn, "tap%d", tap_i);
         // final norm on the tap + cls split (vision_transformer.py:318-321)
-        layernorm(L, dt, x, wf("norm.w", D), wf("norm.b", D), buf(tn), p.Mp, D, 1e-6f, p.N, 1);
+        layernorm(L, dt, x, wf("norm.w", D), wf("norm.b", D), buf(tn), p.Mp, D, 1e-6f, g.no_cls ? 0 : p.N, g.no_cls ? 0 : 1);
         snapshot(tn, buf(tn), false, p.Mp, D, D);
         ++tap_i;
       }
@@ -601,7 +601,7 @@ struct Fwd {
     void* t3 = buf("rb.t3");
     if (!L.ok()) return;
     EDV_DISPATCH_T(dt, {
-      tokens_to_patches_kernel<T><<<nblk(p.Mp * (D / 4), 256), 256, 0, L.stream>>>(x, (T*)pt, p.Mp, p.P, D);
+      tokens_to_patches_kernel<T><<<nblk(p.Mp * (D / 4), 256), 256, 0, L.stream>>>(x, (T*)pt, p.Mp, p.P, D, c->cfg.no_cls ? 0 : 1);
     });
     L.check("tokens_to_patches");
     linear(pt, p.Mp, D, n + "res.c1.w", bcp, ep(t1, bcp, nullptr));
@@ -616,7 +616,7 @@ struct Fwd {
     }
     linear(t2, p.Mp, bcp, n + "res.c3.w", D, ep(t3, D, nullptr));
     if (L.ok()) {
-      EDV_DISPATCH_T(dt, { resblock_add_kernel<T><<<nblk(p.Mp * 32, 256), 256, 0, L.stream>>>(x, (const T*)t3, wf(n + "res.n3.w", D), wf(n + "res.n3.b", D), p.Mp, p.P, D, 1e-6f); });
+      EDV_DISPATCH_T(dt, { resblock_add_kernel<T><<<nblk(p.Mp * 32, 256), 256, 0, L.stream>>>(x, (const T*)t3, wf(n + "res.n3.w", D), wf(n + "res.n3.b", D), p.Mp, p.P, D, 1e-6f, c->cfg.no_cls ? 0 : 1); });
       L.check("res add");
     }
   }
@@ -706,7 +706,7 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
   if (H < 1 || W < 1) return set_err(ctx, EDV_ERR_ARG, "edv_plan: bad frame size");
   Plan p;
   p.B = B; p.T = T; p.H = H; p.W = W; p.h = net_h; p.w = net_w;
-  p.BT = B * T; p.ph = net_h / 14; p.pw = net_w / 14; p.P = p.ph * p.pw; p.N = p.P + 1;
+  p.BT = B * T; p.ph = net_h / 14; p.pw = net_w / 14; p.P = p.ph * p.pw; p.N = p.P + (g.no_cls ? 0 : 1);
   p.M = (long long)p.BT * p.N; p.Mp = (long long)p.BT * p.P;
   p.ph2 = (p.ph - 1) / 2 + 1; p.pw2 = (p.pw - 1) / 2 + 1;
   if (p.M * 4LL * g.dim > 2000000000LL * 4) return set_err(ctx, EDV_ERR_ARG, "edv_plan: clip batch too large for 32-bit row indexing");

@@ -52,11 +52,13 @@ def _lora_entries(prefix, n_in, n_out, lora_type, r):
 
 
 def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_type, residual_block_indexes,
-                     temporal_lora, disable_conv_head, motion=True, head_prefix="head."):
+                     temporal_lora, disable_conv_head, motion=True, head_prefix="head.", include_cls_token=True):
     """Ordered ``[(state_dict key, shape, init kind)]`` reproducing the reference's checkpoint
     layout.  ``init kind`` is only used for fresh random models.
     ``motion=False, head_prefix="depth_head."`` is the layout of the ``endodac`` image model
-    (models/endodac/endodac.py:14-127,213-216): the same DPT head without temporal modules."""
+    (models/endodac/endodac.py:14-127,213-216): the same DPT head without temporal modules.
+    ``include_cls_token`` does not change the layout: the reference keeps ``cls_token`` and the full ``pos_embed`` in the
+    state_dict even when the forward ignores them (vision_transformer.py:170-176)."""
     sz = _MODEL_SIZES[encoder]
     D, F, oc = sz["dim"], features, list(out_channels)
     L = []
@@ -230,8 +232,6 @@ class endodav(nn.Module):
             raise NotImplementedError("use_bn=True is not used by any reference script and is not built")
         if use_clstoken:
             raise NotImplementedError("use_clstoken=True (readout projects) is not used by the reference and is not built")
-        if not include_cls_token:
-            raise NotImplementedError("include_cls_token=False is not built")
         if lora_type not in ("none", "lora", "dvlora", "ssb", "dash"):
             raise ValueError("unknown lora_type %r" % (lora_type,))
         if pe not in ("ape", "rope"):
@@ -242,7 +242,8 @@ class endodav(nn.Module):
         self.intermediate_layer_idx = {'vits': [2, 5, 8, 11], 'vitl': [4, 11, 17, 23]}
         self._cfg = dict(encoder=encoder, features=features, out_channels=list(out_channels), num_frames=num_frames,
                          pe=pe, r=r, lora_type=lora_type, residual_block_indexes=list(residual_block_indexes),
-                         temporal_lora=temporal_lora, disable_conv_head=disable_conv_head)
+                         temporal_lora=temporal_lora, disable_conv_head=disable_conv_head,
+                         include_cls_token=bool(include_cls_token))
         self._inv_sigmoid = bool(inv_sigmoid)
         self._out_sigmoid = bool(out_sigmoid)
         self._dtype_name = (dtype or os.environ.get("ENDODAV_DTYPE", "fp16")).lower()
@@ -285,6 +286,7 @@ class endodav(nn.Module):
         c.engine = self._engine_kind
         c.no_motion = 0 if self._cfg.get("motion", True) else 1
         c.no_normalize = 0 if getattr(self, "_normalize", True) else 1
+        c.no_cls = 0 if self._cfg.get("include_cls_token", True) else 1
         return c
 
     def _pack_state_dict(self):

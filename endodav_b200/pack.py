@@ -262,7 +262,10 @@ def pos_tables(sd, cfg, ph, pw):
     pos = sd["pretrained.pos_embed"].detach().float().cpu()
     n0 = pos.shape[1] - 1
     dim = pos.shape[-1]
-    if not (ph * pw == n0 and ph == pw):
+    # include_cls_token=False: the reference's short-circuit compares x.shape[1] - 1 (one less than the patch count without
+    # a cls token) with N0, so it never triggers and the table is always interpolated (vision_transformer.py:188-191)
+    no_cls = not cfg.get("include_cls_token", True)
+    if no_cls or not (ph * pw == n0 and ph == pw):
         s = int(math.sqrt(n0))
         sx, sy = float(ph + 0.1) / math.sqrt(n0), float(pw + 0.1) / math.sqrt(n0)
         patch = Fn.interpolate(pos[:, 1:].reshape(1, s, s, dim).permute(0, 3, 1, 2), scale_factor=(sx, sy),

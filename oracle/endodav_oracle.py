@@ -116,11 +116,13 @@ def lora_linear_unmerged(c, x, prefix, lora_type):
     return out
 
 
-def interpolate_pos_embed(pos_embed, ph, pw):
+def interpolate_pos_embed(pos_embed, ph, pw, include_cls=True):
     """vision_transformer.py:186-217 (called with w=H, h=W at :220,227): bicubic,
-    align_corners=False, *scale_factor* = ((ph+0.1)/sqrt(N0), (pw+0.1)/sqrt(N0))."""
+    align_corners=False, *scale_factor* = ((ph+0.1)/sqrt(N0), (pw+0.1)/sqrt(N0)).
+    include_cls=False (:214-217): only the patch rows are returned, and the raw-table short-circuit (:190, which
+    compares ``x.shape[1] - 1`` -- one less than the patch count when there is no cls token) can never trigger."""
     n0 = pos_embed.shape[1] - 1
-    if ph * pw == n0 and ph == pw:
+    if include_cls and ph * pw == n0 and ph == pw:
         return pos_embed
     pe = pos_embed.float()
     cls_pe, patch_pe = pe[:, 0], pe[:, 1:]
@@ -132,6 +134,8 @@ def interpolate_pos_embed(pos_embed, ph, pw):
     )
     assert patch_pe.shape[-2] == ph and patch_pe.shape[-1] == pw
     patch_pe = patch_pe.permute(0, 2, 3, 1).reshape(1, -1, dim)
+    if not include_cls:
+        return patch_pe
     return torch.cat((cls_pe.unsqueeze(0), patch_pe), dim=1)
 
 
@@ -164,8 +168,10 @@ def encoder_taps(c, x_norm, unmerged=False):
     p = "pretrained."
     x = c.conv(x_norm, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=14)
     x = x.flatten(2).transpose(1, 2)  # [BT, P, D]
-    x = torch.cat((sd[p + "cls_token"].expand(BT, -1, -1), x), dim=1)
-    x = x + interpolate_pos_embed(sd[p + "pos_embed"], ph, pw)
+    cls = 1 if cfg.get("include_cls_token", True) else 0   # vision_transformer.py:225-227
+    if cls:
+        x = torch.cat((sd[p + "cls_token"].expand(BT, -1, -1), x), dim=1)
+    x = x + interpolate_pos_embed(sd[p + "pos_embed"], ph, pw, bool(cls))
     c.rec("tokens0", x)
     N = x.shape[1]
     lt = cfg["lora_type"]
@@ -190,14 +196,14 @@ def encoder_taps(c, x_norm, unmerged=False):
         x = x + y * sd[b + "ls2.gamma"]
         if i in cfg["residual_block_indexes"]:
             # block.py:146-150 -- patch_h/patch_w are fixed at construction (224x280 only)
-            pe_ = x[:, 1:, :].reshape(BT, ph, pw, D).permute(0, 3, 1, 2)
-            r_ = _res_bottleneck(c, pe_, b + "residual_.").permute(0, 2, 3, 1).reshape(BT, N - 1, D)
-            x = torch.cat((x[:, :1], x[:, 1:] + r_), dim=1)
+            pe_ = x[:, cls:, :].reshape(BT, ph, pw, D).permute(0, 3, 1, 2)
+            r_ = _res_bottleneck(c, pe_, b + "residual_.").permute(0, 2, 3, 1).reshape(BT, N - cls, D)
+            x = torch.cat((x[:, :cls], x[:, cls:] + r_), dim=1)
         if i in (0,):
             c.rec("block0", x)
         if i in (cfg.get("taps") or TAPS[cfg["encoder"]]):
             t = F.layer_norm(x, (D,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
-            taps.append(t[:, 1:])
+            taps.append(t[:, cls:])   # vision_transformer.py:319-324
     for i, t in enumerate(taps):
         c.rec("tap%d" % i, t)
     return taps

@@ -41,6 +41,10 @@ FORWARD_CASES = {
     "fwd_vits_dash_tlora": (dict(encoder="vits", lora_type="dash", temporal_lora=True), (42, 56), (1, 3, 48, 64), 41, 42),
     "fwd_vits_rope": (dict(encoder="vits", lora_type="dvlora", pe="rope"), (42, 56), (1, 5, 42, 56), 51, 52),
     "fwd_vitl": (dict(encoder="vitl", lora_type="dvlora"), (70, 84), (1, 2, 70, 84), 61, 62),
+    # include_cls_token=False: the ViT runs on the patch tokens only (every reference script plumbs opt.include_cls_token)
+    "fwd_vits_nocls": (dict(encoder="vits", lora_type="dvlora", include_cls_token=False), (42, 56), (1, 3, 48, 64), 81, 82),
+    "fwd_vits_nocls_res": (dict(encoder="vits", lora_type="lora", residual_block_indexes=[2, 5, 8, 11], include_cls_token=False),
+                           (224, 280), (1, 2, 224, 280), 83, 84),
 }
 
 # Full-size BASELINE configurations (2: ViT-S 32 x 518 x 518; 4: ViT-L at 518 x 518, two frames): the reference output
@@ -128,7 +132,7 @@ def ctor_kwargs(over, image_shape):
 
 def oracle_cfg(kw):
     keys = ("encoder", "features", "out_channels", "num_frames", "pe", "r", "lora_type",
-            "residual_block_indexes", "temporal_lora", "disable_conv_head")
+            "residual_block_indexes", "temporal_lora", "disable_conv_head", "include_cls_token")
     return weights.full_cfg({k: kw[k] for k in keys if k in kw})
 
 
@@ -225,7 +229,13 @@ def main():
         with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
             json.dump(manifest, f, indent=1)
         return
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]   # add cases without regenerating the others
+    if only:
+        with open(os.path.join(GOLDEN_DIR, "manifest.json")) as f:
+            manifest = json.load(f)
     for name, (over, ishape, (B, T, H, W), wseed, fseed) in FORWARD_CASES.items():
+        if only and name not in only:
+            continue
         kw = ctor_kwargs(over, ishape)
         cfg = oracle_cfg(kw)
         sd = weights.make_state_dict(cfg, wseed)
@@ -236,7 +246,7 @@ def main():
         with torch.no_grad():
             out = model(x)
         arrays = {"disp%d" % s: out[("disp", s)].numpy().astype(np.float32) for s in range(4)}
-        if name == "fwd_vits_lora_res_convhead":  # keep the fixture small
+        if name in ("fwd_vits_lora_res_convhead", "fwd_vits_nocls_res"):  # keep the fixture small
             arrays["disp0"] = arrays["disp0"][:, :, ::4, ::4].copy()
             arrays["disp1"] = arrays["disp1"][:, :, ::2, ::2].copy()
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
@@ -254,6 +264,10 @@ def main():
             with open(os.path.join(GOLDEN_DIR, "state_dict_keys_vits_lora_res_convhead.json"), "w") as f:
                 json.dump([[k, list(v.shape)] for k, v in model.state_dict().items()], f)
         del model
+    if only:
+        with open(os.path.join(GOLDEN_DIR, "manifest.json"), "w") as f:
+            json.dump(manifest, f, indent=1)
+        return
 
     for name, (N, H, W, ishape, wseed, fseed) in VIDEO_CASES.items():
         kw = ctor_kwargs(dict(encoder="vits", lora_type="dvlora"), ishape)

@@ -40,6 +40,7 @@ DEFAULT_CFG = dict(
     motion=True,   # False: the endodac image model (same head, no temporal modules)
     taps=None,     # None: the encoder's table (endodav.py:76-79)
     lora_scale=2.0,  # lora_type="lora": alpha/r with alpha = 2r (endodav.py:111)
+    include_cls_token=True,  # False: a ViT without the cls token (vision_transformer.py:214-228,319-324; block.py:131-133)
 )
 
 

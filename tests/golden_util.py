@@ -8,7 +8,7 @@ from oracle import weights
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ORACLE_KEYS = ("encoder", "features", "out_channels", "num_frames", "pe", "r", "lora_type",
-               "residual_block_indexes", "temporal_lora", "disable_conv_head")
+               "residual_block_indexes", "temporal_lora", "disable_conv_head", "include_cls_token")
 
 
 def manifest():
@@ -28,7 +28,7 @@ def oracle_cfg(ctor):
 
 def subsample_like_golden(name, s, arr):
     """make_golden.py stores a strided view of the two largest maps of one case."""
-    if name == "fwd_vits_lora_res_convhead":
+    if name in ("fwd_vits_lora_res_convhead", "fwd_vits_nocls_res"):
         if s == 0:
             return arr[:, :, ::4, ::4]
         if s == 1:

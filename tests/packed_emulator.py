@@ -45,7 +45,8 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
     BT = B * T
     h, w = image_shape
     ph, pw = h // 14, w // 14
-    P, N = ph * pw, ph * pw + 1
+    cls = 1 if cfg.get("include_cls_token", True) else 0
+    P, N = ph * pw, ph * pw + cls
     Fe = cfg["features"]
     oc = cfg["out_channels"]
     cp = [(c + 63) // 64 * 64 for c in oc]
@@ -62,7 +63,10 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
     A0 = F.unfold(xn, kernel_size=14, stride=14).transpose(1, 2).reshape(BT * P, 588)
     A0 = F.pad(A0, (0, pk["patch.w"].shape[1] - 588))
     tok = _lin(A0, pk["patch.w"]).reshape(BT, P, D) + pk["patch.pos"][None]
-    xs = torch.cat([pk["cls_row"].reshape(1, 1, D).expand(BT, 1, D), tok], 1).reshape(BT * N, D)
+    if cls:
+        xs = torch.cat([pk["cls_row"].reshape(1, 1, D).expand(BT, 1, D), tok], 1).reshape(BT * N, D)
+    else:   # include_cls_token=False (edv_config.no_cls): patch tokens only
+        xs = tok.reshape(BT * N, D)
     rec("tokens0", xs.reshape(BT, N, D))
     tap_out = []
     for i in range(depth):
@@ -77,7 +81,7 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
         xs = xs + _lin(hh, pk[n + "fc2.w"], pk[n + "fc2.b"])
         if i in cfg.get("residual_block_indexes", []):
             bc = D // 8
-            pt = xs.reshape(BT, N, D)[:, 1:].reshape(BT * P, D)
+            pt = xs.reshape(BT, N, D)[:, cls:].reshape(BT * P, D)
             t1 = _lin(pt, pk[n + "res.c1.w"])
             bcp = t1.shape[1]
 
@@ -98,12 +102,12 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
             s = (t3 - u).pow(2).mean(1, keepdim=True)
             t3 = (t3 - u) / torch.sqrt(s + 1e-6) * pk[n + "res.n3.w"] + pk[n + "res.n3.b"]
             x3 = xs.reshape(BT, N, D).clone()
-            x3[:, 1:] += t3.reshape(BT, P, D)
+            x3[:, cls:] += t3.reshape(BT, P, D)
             xs = x3.reshape(BT * N, D)
         if i == 0:
             rec("block0", xs.reshape(BT, N, D))
         if i in taps:
-            t = F.layer_norm(xs, (D,), pk["norm.w"], pk["norm.b"], 1e-6).reshape(BT, N, D)[:, 1:].reshape(BT * P, D)
+            t = F.layer_norm(xs, (D,), pk["norm.w"], pk["norm.b"], 1e-6).reshape(BT, N, D)[:, cls:].reshape(BT * P, D)
             rec("tap%d" % len(tap_out), t.reshape(BT, P, D))
             tap_out.append(t)
     L1 = _pixshuf(_lin(tap_out[0], pk["proj0.w"], pk["proj0.b"]), BT, ph, pw, 4, cp[0])
