@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     live[rw] = mo[rw] < Mout;
     long long mi = mo[rw];
     if (grp > 0) {
-      const int per = grp - skip;
-      mi = (mo[rw] / per) * grp + skip + (mo[rw] % per);
+      // skip >= 0: drop the first `skip` rows of every group of `grp`; skip < 0: keep ONLY the first -skip rows
+      const int per = skip >= 0 ? grp - skip : -skip;
+      mi = (mo[rw] / per) * grp + (skip >= 0 ? skip : 0) + (mo[rw] % per);
     }
     const float* xr = x + mi * D;
 #pragma unroll

@@ -477,6 +477,29 @@ struct Fwd {
         // final norm on the tap + cls split (vision_transformer.py:318-321)
         layernorm(L, dt, x, wf("norm.w", D), wf("norm.b", D), buf(tn), p.Mp, D, 1e-6f, g.no_cls ? 0 : p.N, g.no_cls ? 0 : 1);
         snapshot(tn, buf(tn), false, p.Mp, D, D);
+        if (g.use_clstoken) {
+          // readout projects (dpt.py:92-99; dpt_pyramid.py:54-57): tap' = GELU(Linear(2D, D)([token | class token])) =
+          // GELU(token W1^T + rb[frame]) with the per-frame row bias rb = class token W2^T + b.  The class token is row 0
+          // of the frame after the final norm (without a cls token: its first patch token, as in the reference).
+          char cn[16], rn_[16], on[16];
+          snprintf(cn, sizeof cn, "tapc%d", tap_i);
+          snprintf(rn_, sizeof rn_, "rorb%d", tap_i);
+          snprintf(on, sizeof on, "tapr%d", tap_i);
+          const std::string ro = "ro" + std::to_string(tap_i) + ".";
+          layernorm(L, dt, x, wf("norm.w", D), wf("norm.b", D), buf(cn), p.BT, D, 1e-6f, p.N, -1);
+          {
+            Epi e = ep(buf(rn_), D, wf(ro + "b", D));
+            e.out_f32 = 1;
+            linear(buf(cn), p.BT, D, ro + "w2", D, e);
+          }
+          {
+            Epi e = ep(buf(on), D, nullptr);
+            e.rowbias = (const float*)buf(rn_);
+            e.rb_div = p.P; e.rb_mod = p.BT; e.rb_ld = D;
+            e.act = ACT_GELU;
+            linear(buf(tn), p.Mp, D, ro + "w1", D, e);
+          }
+        }
         ++tap_i;
       }
     }
@@ -503,14 +526,14 @@ struct Fwd {
       // projects[0] (1x1) merged with resize_layers[0] (ConvT k4 s4): one GEMM + pixel shuffle
       Epi e = ep(L1, p.Cp[0], wf("proj0.b", 16 * p.Cp[0]));
       e.map = MAP_PIXSHUF; e.ps_k = 4; e.ps_h = p.ph; e.ps_w = p.pw; e.ps_c = p.Cp[0];
-      linear(buf("tap0"), p.Mp, D, "proj0.w", 16 * p.Cp[0], e);
+      linear(buf(g.use_clstoken ? "tapr0" : "tap0"), p.Mp, D, "proj0.w", 16 * p.Cp[0], e);
     }
     {
       Epi e = ep(L2, p.Cp[1], wf("proj1.b", 4 * p.Cp[1]));
       e.map = MAP_PIXSHUF; e.ps_k = 2; e.ps_h = p.ph; e.ps_w = p.pw; e.ps_c = p.Cp[1];
-      linear(buf("tap1"), p.Mp, D, "proj1.w", 4 * p.Cp[1], e);
+      linear(buf(g.use_clstoken ? "tapr1" : "tap1"), p.Mp, D, "proj1.w", 4 * p.Cp[1], e);
     }
-    linear(buf("tap2"), p.Mp, D, "proj2.w", p.Cp[2], ep(L3, p.Cp[2], wf("proj2.b", p.Cp[2])));
+    linear(buf(g.use_clstoken ? "tapr2" : "tap2"), p.Mp, D, "proj2.w", p.Cp[2], ep(L3, p.Cp[2], wf("proj2.b", p.Cp[2])));
     if (mm_on) motion(0, L3, L3m, par ? "mmb." : "mm.");
     // scratch.layer{1-4}_rn (3x3, no bias) -> F channels, plus relu copies for the RCUs
     {
@@ -522,7 +545,7 @@ struct Fwd {
       conv3(L1, p.BT, 4 * p.ph, 4 * p.pw, p.Cp[0], "rn1.w", F_, e);
     }
     back_to_main();
-    linear(buf("tap3"), p.Mp, D, "proj3.w", p.Cp[3], ep(L4p, p.Cp[3], wf("proj3.b", p.Cp[3])));
+    linear(buf(g.use_clstoken ? "tapr3" : "tap3"), p.Mp, D, "proj3.w", p.Cp[3], ep(L4p, p.Cp[3], wf("proj3.b", p.Cp[3])));
     {
       // resize_layers[3]: 3x3 stride 2 pad 1 (dpt.py:85-90) = explicit im2col + GEMM
       const long long Mo = (long long)p.BT * p.ph2 * p.pw2;
@@ -758,6 +781,15 @@ int edv_plan(edv_ctx* ctx, int B, int T, int H, int W, int net_h, int net_w, siz
     char n[8];
     snprintf(n, sizeof n, "tap%d", i);
     add(n, (size_t)p.Mp * D * es);
+    if (g.use_clstoken) {
+      char m[16];
+      snprintf(m, sizeof m, "tapc%d", i);
+      add(m, (size_t)p.BT * D * es);
+      snprintf(m, sizeof m, "rorb%d", i);
+      add(m, (size_t)p.BT * D * 4, 4);
+      snprintf(m, sizeof m, "tapr%d", i);
+      add(m, (size_t)p.Mp * D * es);
+    }
   }
   if (g.res_blocks) {
     const int bcp = round_up(D / 8, 64);

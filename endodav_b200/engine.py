@@ -16,7 +16,7 @@ DTYPES = {"fp32": EDV_F32, "f32": EDV_F32, "float32": EDV_F32, "bf16": EDV_BF16,
           "fp16": EDV_F16, "f16": EDV_F16, "float16": EDV_F16}
 TORCH_DTYPE = {EDV_F32: torch.float32, EDV_BF16: torch.bfloat16, EDV_F16: torch.float16}
 
-ABI_VERSION = 11   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
+ABI_VERSION = 12   # must equal EDV_ABI_VERSION of include/endodav_b200.h (argtypes below are mirrored by hand)
 
 EXPORTS = [
     "edv_abi_version", "edv_create", "edv_destroy", "edv_last_error", "edv_set_weight", "edv_plan", "edv_forward", "edv_forward_u8",
@@ -34,7 +34,7 @@ class EdvConfig(ctypes.Structure):
         ("features", ctypes.c_int32), ("out_channels", ctypes.c_int32 * 4), ("num_frames", ctypes.c_int32),
         ("conv_head", ctypes.c_int32), ("out_sigmoid", ctypes.c_int32), ("inv_sigmoid", ctypes.c_int32),
         ("res_blocks", ctypes.c_int32), ("rope", ctypes.c_int32), ("dtype", ctypes.c_int32), ("engine", ctypes.c_int32),
-        ("no_motion", ctypes.c_int32), ("no_normalize", ctypes.c_int32), ("no_cls", ctypes.c_int32),
+        ("no_motion", ctypes.c_int32), ("no_normalize", ctypes.c_int32), ("use_clstoken", ctypes.c_int32), ("no_cls", ctypes.c_int32),
     ]
 
 

@@ -52,7 +52,7 @@ def _lora_entries(prefix, n_in, n_out, lora_type, r):
 
 
 def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_type, residual_block_indexes,
-                     temporal_lora, disable_conv_head, motion=True, head_prefix="head.", include_cls_token=True):
+                     temporal_lora, disable_conv_head, motion=True, head_prefix="head.", include_cls_token=True, use_bn=False, use_clstoken=False):
     """Ordered ``[(state_dict key, shape, init kind)]`` reproducing the reference's checkpoint
     layout.  ``init kind`` is only used for fresh random models.
     ``motion=False, head_prefix="depth_head."`` is the layout of the ``endodac`` image model
@@ -90,6 +90,9 @@ def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_ty
     L += [(h + "resize_layers.0.weight", (oc[0], oc[0], 4, 4), "kaiming"), (h + "resize_layers.0.bias", (oc[0],), "zeros"),
           (h + "resize_layers.1.weight", (oc[1], oc[1], 2, 2), "kaiming"), (h + "resize_layers.1.bias", (oc[1],), "zeros"),
           (h + "resize_layers.3.weight", (oc[3], oc[3], 3, 3), "kaiming"), (h + "resize_layers.3.bias", (oc[3],), "zeros")]
+    if use_clstoken:   # dpt.py:92-99, registered between resize_layers and scratch
+        for i in range(4):
+            L += [(h + "readout_projects.%d.0.weight" % i, (D, 2 * D), "linear"), (h + "readout_projects.%d.0.bias" % i, (D,), "zeros")]
     s = h + "scratch."
     for i in range(4):
         L += [(s + "layer%d_rn.weight" % (i + 1), (F, oc[i], 3, 3), "kaiming")]
@@ -100,6 +103,11 @@ def parameter_layout(encoder, features, out_channels, num_frames, pe, r, lora_ty
             for c in (1, 2):
                 L += [(rn + "resConfUnit%d.conv%d.weight" % (u, c), (F, F, 3, 3), "kaiming"),
                       (rn + "resConfUnit%d.conv%d.bias" % (u, c), (F,), "zeros")]
+            if use_bn:   # registration order of ResidualConvUnit.__init__ (util/blocks.py:49-59): conv1, conv2, bn1, bn2
+                for c in (1, 2):
+                    b = rn + "resConfUnit%d.bn%d." % (u, c)
+                    L += [(b + "weight", (F,), "ones"), (b + "bias", (F,), "zeros"), (b + "running_mean", (F,), "buffer_zeros"),
+                          (b + "running_var", (F,), "buffer_ones"), (b + "num_batches_tracked", (), "buffer_count")]
     if disable_conv_head:
         L += [(s + "output_conv1.weight", (F // 2, F, 3, 3), "kaiming"), (s + "output_conv1.bias", (F // 2,), "zeros"),
               (s + "output_conv2.0.weight", (32, F // 2, 3, 3), "kaiming"), (s + "output_conv2.0.bias", (32,), "zeros"),
@@ -228,10 +236,6 @@ class endodav(nn.Module):
         super().__init__()
         if encoder not in _MODEL_SIZES:
             raise KeyError(encoder)  # the reference indexes its backbone table the same way (endodav.py:80-91)
-        if use_bn:
-            raise NotImplementedError("use_bn=True is not used by any reference script and is not built")
-        if use_clstoken:
-            raise NotImplementedError("use_clstoken=True (readout projects) is not used by the reference and is not built")
         if lora_type not in ("none", "lora", "dvlora", "ssb", "dash"):
             raise ValueError("unknown lora_type %r" % (lora_type,))
         if pe not in ("ape", "rope"):
@@ -243,7 +247,7 @@ class endodav(nn.Module):
         self._cfg = dict(encoder=encoder, features=features, out_channels=list(out_channels), num_frames=num_frames,
                          pe=pe, r=r, lora_type=lora_type, residual_block_indexes=list(residual_block_indexes),
                          temporal_lora=temporal_lora, disable_conv_head=disable_conv_head,
-                         include_cls_token=bool(include_cls_token))
+                         include_cls_token=bool(include_cls_token), use_bn=bool(use_bn), use_clstoken=bool(use_clstoken))
         self._inv_sigmoid = bool(inv_sigmoid)
         self._out_sigmoid = bool(out_sigmoid)
         self._dtype_name = (dtype or os.environ.get("ENDODAV_DTYPE", "fp16")).lower()
@@ -253,6 +257,9 @@ class endodav(nn.Module):
         for key, shape, kind in parameter_layout(**self._cfg):
             if kind == "buffer_pe":
                 _attach(self, key, _sinusoid(shape[2], shape[1]), True)
+            elif kind in ("buffer_zeros", "buffer_ones", "buffer_count"):   # BatchNorm running statistics (use_bn=True)
+                _attach(self, key, torch.zeros(shape) if kind == "buffer_zeros" else torch.ones(shape) if kind == "buffer_ones"
+                        else torch.tensor(0, dtype=torch.long), True)
             else:
                 _attach(self, key, _init_tensor(shape, kind), False)
         _listify(self)
@@ -287,6 +294,7 @@ class endodav(nn.Module):
         c.no_motion = 0 if self._cfg.get("motion", True) else 1
         c.no_normalize = 0 if getattr(self, "_normalize", True) else 1
         c.no_cls = 0 if self._cfg.get("include_cls_token", True) else 1
+        c.use_clstoken = 1 if self._cfg.get("use_clstoken", False) else 0
         return c
 
     def _pack_state_dict(self):

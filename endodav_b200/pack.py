@@ -174,6 +174,13 @@ def pack_state_dict(sd, cfg, dtype=torch.bfloat16):
         vec("proj%d.b" % i, _pad_vec(sd[h + "projects.%d.bias" % i], cp[i]))
     mat("resize3.w", _conv3_to_gemm(sd[h + "resize_layers.3.weight"].double(), cp[3], cp[3]))
     vec("resize3.b", _pad_vec(sd[h + "resize_layers.3.bias"], cp[3]))
+    if cfg.get("use_clstoken"):
+        # readout projects (dpt.py:92-99): Linear(2D, D) on [token | class token] = token W1^T + (class token W2^T + b)
+        for i in range(4):
+            w_ = sd[h + "readout_projects.%d.0.weight" % i].double()
+            mat("ro%d.w1" % i, w_[:, :D])
+            mat("ro%d.w2" % i, w_[:, D:])
+            vec("ro%d.b" % i, sd[h + "readout_projects.%d.0.bias" % i])
     s = h + "scratch."
     for i in range(4):
         mat("rn%d.w" % (i + 1), _conv3_to_gemm(sd[s + "layer%d_rn.weight" % (i + 1)].double(), cp[i]))
@@ -184,8 +191,17 @@ def pack_state_dict(sd, cfg, dtype=torch.bfloat16):
         vec(n + "out.b", sd[rn + "out_conv.bias"])
         for u in (1, 2):
             for c in (1, 2):
-                mat(n + "rcu%d.c%d.w" % (u, c), _conv3_to_gemm(sd[rn + "resConfUnit%d.conv%d.weight" % (u, c)].double(), F))
-                vec(n + "rcu%d.c%d.b" % (u, c), sd[rn + "resConfUnit%d.conv%d.bias" % (u, c)])
+                w_ = sd[rn + "resConfUnit%d.conv%d.weight" % (u, c)].double()
+                b_ = sd[rn + "resConfUnit%d.conv%d.bias" % (u, c)].double()
+                bn = rn + "resConfUnit%d.bn%d." % (u, c)
+                if bn + "weight" in sd:
+                    # use_bn=True: eval-mode BatchNorm2d (util/blocks.py:80-81,85-86; eps 1e-5) is an affine map per output
+                    # channel -> folded into the conv: W' = W s, b' = (b - running_mean) s + beta, s = gamma / sqrt(var + eps)
+                    sc = sd[bn + "weight"].double() / torch.sqrt(sd[bn + "running_var"].double() + 1e-5)
+                    w_ = w_ * sc[:, None, None, None]
+                    b_ = (b_ - sd[bn + "running_mean"].double()) * sc + sd[bn + "bias"].double()
+                mat(n + "rcu%d.c%d.w" % (u, c), _conv3_to_gemm(w_, F))
+                vec(n + "rcu%d.c%d.b" % (u, c), b_)
 
     def head(c0, c2, c4, k0, k2, k4):
         mat(c0 + ".w", _conv3_to_gemm(sd[k0 + ".weight"].double(), F))

@@ -30,7 +30,7 @@ typedef struct edv_ctx edv_ctx;
 /* Bumped whenever an entry point's argument list or a struct layout changes.  The ctypes host
  * (endodav_b200/engine.py) mirrors the signatures by hand, so it refuses a library whose
  * edv_abi_version() differs from its own constant instead of calling it with a stale layout. */
-#define EDV_ABI_VERSION 11
+#define EDV_ABI_VERSION 12
 int edv_abi_version(void);
 
 enum edv_status {
@@ -69,6 +69,7 @@ typedef struct edv_config {
   int32_t engine;          /* edv_engine */
   int32_t no_motion;       /* 1: no temporal modules -- the `endodac` image model (models/endodac/endodac.py:14-127) */
   int32_t no_normalize;    /* 1: frames enter the patch embedding un-normalised (endodac pre_norm=False, endodac.py:208-211) */
+  int32_t use_clstoken;    /* 1: readout projects (dpt.py:92-99; dpt_pyramid.py:54-57): tap' = GELU(Linear(2D, D)([token | class token])) */
   int32_t no_cls;          /* 1: include_cls_token=False -- the ViT runs on the patch tokens only (vision_transformer.py:214-228,
                               319-324; block.py:131-133): S = P tokens, no cls row, pos-embed = the patch rows */
 } edv_config;

@@ -176,6 +176,7 @@ def encoder_taps(c, x_norm, unmerged=False):
     N = x.shape[1]
     lt = cfg["lora_type"]
     taps = []
+    cls_rows = []
     for i in range(enc["depth"]):
         b = p + "blocks.%d." % i
         y = F.layer_norm(x, (D,), sd[b + "norm1.weight"], sd[b + "norm1.bias"], 1e-6)
@@ -204,8 +205,10 @@ def encoder_taps(c, x_norm, unmerged=False):
         if i in (cfg.get("taps") or TAPS[cfg["encoder"]]):
             t = F.layer_norm(x, (D,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
             taps.append(t[:, cls:])   # vision_transformer.py:319-324
+            cls_rows.append(t[:, 0])  # the class token (without a cls token: the first patch token, "not real cls tokens")
     for i, t in enumerate(taps):
         c.rec("tap%d" % i, t)
+    c.cls_rows = cls_rows
     return taps
 
 
@@ -276,8 +279,14 @@ def _apply_rope(q, k, dim, T, theta=10000.0):
 def _rcu(c, x, p):
     """ResidualConvUnit, util/blocks.py:78-91."""
     sd = c.sd
-    o = c.conv(F.relu(x), sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
-    o = c.conv(F.relu(o), sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+
+    def bn(o, q):   # nn.BatchNorm2d in eval mode (util/blocks.py:80-81,85-86): running statistics, eps 1e-5
+        if q + "weight" not in sd:
+            return o
+        return F.batch_norm(o, sd[q + "running_mean"], sd[q + "running_var"], sd[q + "weight"], sd[q + "bias"], False, 0.0, 1e-5)
+
+    o = bn(c.conv(F.relu(x), sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1), p + "bn1.")
+    o = bn(c.conv(F.relu(o), sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1), p + "bn2.")
     return o + x
 
 
@@ -312,6 +321,11 @@ def dpt_head(c, taps, ph, pw, T, unmerged=False, inv_sigmoid=False, out_sigmoid=
     B = BT // T
     outs = []
     for i, x in enumerate(taps):
+        if cfg.get("use_clstoken"):
+            # dpt_pyramid.py:54-57: Linear(2D, D) + GELU on [token | class token of its frame]
+            readout = c.cls_rows[i].unsqueeze(1).expand_as(x)
+            x = F.gelu(c.linear(torch.cat((x, readout), -1), sd[h + "readout_projects.%d.0.weight" % i],
+                                sd[h + "readout_projects.%d.0.bias" % i]))
         x = x.permute(0, 2, 1).reshape(BT, x.shape[-1], ph, pw)
         x = c.conv(x, sd[h + "projects.%d.weight" % i], sd[h + "projects.%d.bias" % i])
         if i == 0:

@@ -42,6 +42,13 @@ FORWARD_CASES = {
     "fwd_vits_rope": (dict(encoder="vits", lora_type="dvlora", pe="rope"), (42, 56), (1, 5, 42, 56), 51, 52),
     "fwd_vitl": (dict(encoder="vitl", lora_type="dvlora"), (70, 84), (1, 2, 70, 84), 61, 62),
     # include_cls_token=False: the ViT runs on the patch tokens only (every reference script plumbs opt.include_cls_token)
+    # use_bn=True: BatchNorm2d (eval mode) after both convs of every ResidualConvUnit
+    "fwd_vits_bn": (dict(encoder="vits", lora_type="dvlora", use_bn=True), (42, 56), (1, 3, 48, 64), 85, 86),
+    # use_clstoken=True: readout projects on [patch token | class token]; the second case takes the "class token" of a ViT
+    # without one (its first patch token)
+    "fwd_vits_clstoken": (dict(encoder="vits", lora_type="dvlora", use_clstoken=True), (42, 56), (1, 3, 48, 64), 87, 88),
+    "fwd_vits_clstoken_nocls": (dict(encoder="vits", lora_type="lora", use_clstoken=True, include_cls_token=False), (42, 56),
+                                (2, 2, 42, 56), 89, 90),
     "fwd_vits_nocls": (dict(encoder="vits", lora_type="dvlora", include_cls_token=False), (42, 56), (1, 3, 48, 64), 81, 82),
     "fwd_vits_nocls_res": (dict(encoder="vits", lora_type="lora", residual_block_indexes=[2, 5, 8, 11], include_cls_token=False),
                            (224, 280), (1, 2, 224, 280), 83, 84),
@@ -132,7 +139,7 @@ def ctor_kwargs(over, image_shape):
 
 def oracle_cfg(kw):
     keys = ("encoder", "features", "out_channels", "num_frames", "pe", "r", "lora_type",
-            "residual_block_indexes", "temporal_lora", "disable_conv_head", "include_cls_token")
+            "residual_block_indexes", "temporal_lora", "disable_conv_head", "include_cls_token", "use_bn", "use_clstoken")
     return weights.full_cfg({k: kw[k] for k in keys if k in kw})
 
 

@@ -40,6 +40,8 @@ DEFAULT_CFG = dict(
     motion=True,   # False: the endodac image model (same head, no temporal modules)
     taps=None,     # None: the encoder's table (endodav.py:76-79)
     lora_scale=2.0,  # lora_type="lora": alpha/r with alpha = 2r (endodav.py:111)
+    use_clstoken=False,  # True: readout projects Linear(2D, D) + GELU on [patch token | cls token] (dpt.py:92-99, dpt_pyramid.py:54-57)
+    use_bn=False,  # True: BatchNorm2d after both convs of every ResidualConvUnit (util/blocks.py:57-59,80-87), eval mode
     include_cls_token=True,  # False: a ViT without the cls token (vision_transformer.py:214-228,319-324; block.py:131-133)
 )
 
@@ -159,6 +161,10 @@ def make_state_dict(cfg=None, seed=1234):
     g.bias(h + "resize_layers.1.bias", oc[1])
     g.weight(h + "resize_layers.3.weight", (oc[3], oc[3], 3, 3))
     g.bias(h + "resize_layers.3.bias", oc[3])
+    if cfg.get("use_clstoken"):
+        for i in range(4):
+            g.weight(h + "readout_projects.%d.0.weight" % i, (D, 2 * D))
+            g.bias(h + "readout_projects.%d.0.bias" % i, D)
     s = h + "scratch."
     for i in range(4):
         g.weight(s + "layer%d_rn.weight" % (i + 1), (F, oc[i], 3, 3))
@@ -171,6 +177,14 @@ def make_state_dict(cfg=None, seed=1234):
                 # residual branches stay smaller than the skip path (as in a trained DPT head)
                 g.weight(rn + "resConfUnit%d.conv%d.weight" % (u, c), (F, F, 3, 3), 0.5)
                 g.bias(rn + "resConfUnit%d.conv%d.bias" % (u, c), F)
+            if cfg.get("use_bn"):
+                for c in (1, 2):   # registration order of ResidualConvUnit.__init__: conv1, conv2, bn1, bn2
+                    b = rn + "resConfUnit%d.bn%d." % (u, c)
+                    g.normal(b + "weight", (F,), 0.2, 1.0)
+                    g.normal(b + "bias", (F,), 0.1)
+                    g.normal(b + "running_mean", (F,), 0.1)
+                    g.uniform(b + "running_var", (F,), 0.5, 1.5)
+                    g.sd[b + "num_batches_tracked"] = torch.tensor(100, dtype=torch.long)
     if cfg["disable_conv_head"]:
         g.weight(s + "output_conv1.weight", (F // 2, F, 3, 3))
         g.bias(s + "output_conv1.bias", F // 2)

@@ -8,7 +8,7 @@ from oracle import weights
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ORACLE_KEYS = ("encoder", "features", "out_channels", "num_frames", "pe", "r", "lora_type",
-               "residual_block_indexes", "temporal_lora", "disable_conv_head", "include_cls_token")
+               "residual_block_indexes", "temporal_lora", "disable_conv_head", "include_cls_token", "use_bn", "use_clstoken")
 
 
 def manifest():

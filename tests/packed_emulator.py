@@ -109,6 +109,11 @@ def forward(pk, cfg, enc, x, image_shape, record=None):
         if i in taps:
             t = F.layer_norm(xs, (D,), pk["norm.w"], pk["norm.b"], 1e-6).reshape(BT, N, D)[:, cls:].reshape(BT * P, D)
             rec("tap%d" % len(tap_out), t.reshape(BT, P, D))
+            if cfg.get("use_clstoken"):   # readout: GELU(tap W1^T + (cls W2^T + b)[frame])
+                k = len(tap_out)
+                crow = F.layer_norm(xs, (D,), pk["norm.w"], pk["norm.b"], 1e-6).reshape(BT, N, D)[:, 0]
+                rb = _lin(crow, pk["ro%d.w2" % k], pk["ro%d.b" % k])
+                t = F.gelu(_lin(t, pk["ro%d.w1" % k]).reshape(BT, P, D) + rb[:, None, :]).reshape(BT * P, D)
             tap_out.append(t)
     L1 = _pixshuf(_lin(tap_out[0], pk["proj0.w"], pk["proj0.b"]), BT, ph, pw, 4, cp[0])
     L2 = _pixshuf(_lin(tap_out[1], pk["proj1.w"], pk["proj1.b"]), BT, ph, pw, 2, cp[1])
