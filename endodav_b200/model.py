@@ -425,12 +425,6 @@ class endodac(endodav):
         assert r > 0                                       # endodac.py:168
         if backbone_size not in self._SIZES:
             raise KeyError(backbone_size)                  # the reference indexes its tables the same way (:200-204)
-        if use_bn:
-            raise NotImplementedError("use_bn=True is not used by any reference script and is not built")
-        if use_cls_token:
-            raise NotImplementedError("use_cls_token=True (readout projects) is not built")
-        if not include_cls_token:
-            raise NotImplementedError("include_cls_token=False is not built")
         if lora_type not in ("none", "lora", "dvlora"):
             # endodac.py:213-224 installs adapters only for these; any other string leaves plain linears
             lora_type = "none"
@@ -443,7 +437,8 @@ class endodac(endodav):
         self._cfg = dict(encoder=self.encoder, features=sz["features"], out_channels=list(sz["out_channels"]),
                          num_frames=32, pe="ape", r=r, lora_type=lora_type,
                          residual_block_indexes=list(residual_block_indexes), temporal_lora=False,
-                         disable_conv_head=disable_conv_head, motion=False)
+                         disable_conv_head=disable_conv_head, motion=False, include_cls_token=bool(include_cls_token),
+                         use_clstoken=bool(use_cls_token), use_bn=bool(use_bn))   # endodac.py:161-163 (its keyword is use_cls_token)
         # forward taps get_intermediate_layers(x, 4): the LAST four blocks (endodac.py:254;
         # vision_transformer.py:292-293), not the [2,5,8,11] table at endodac.py:183-186
         depth = _MODEL_SIZES[self.encoder]["depth"]
@@ -458,7 +453,11 @@ class endodac(endodav):
             raise ValueError("dtype must be one of %s" % sorted(_engine.DTYPES))
         self._engine_kind = {"tc": _engine.ENGINE_TC, "simt": _engine.ENGINE_SIMT}[os.environ.get("ENDODAV_ENGINE", "tc").lower()]
         for key, shape, kind in parameter_layout(head_prefix="depth_head.", **{k: v for k, v in self._cfg.items() if k not in ("taps", "lora_scale")}):
-            _attach(self, key, _init_tensor(shape, kind), False)
+            if kind in ("buffer_zeros", "buffer_ones", "buffer_count"):   # BatchNorm running statistics (use_bn=True)
+                _attach(self, key, torch.zeros(shape) if kind == "buffer_zeros" else torch.ones(shape) if kind == "buffer_ones"
+                        else torch.tensor(0, dtype=torch.long), True)
+            else:
+                _attach(self, key, _init_tensor(shape, kind), False)
         _listify(self)
         self._eng = None
         self._packed_versions = None

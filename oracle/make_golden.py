@@ -80,6 +80,9 @@ ENDODAC_CASES = {
                                   pre_norm=True), (2, 2, 3, 56, 56), 73, 74),
     "dac_base_lora_convhead": (dict(backbone_size="base", lora_type="lora", image_shape=(56, 70), disable_conv_head=False,
                                     inv_sigmoid=True), (2, 3, 56, 70), 75, 76),
+    # the three constructor modes endodac shares with endodav: no cls token, readout projects, BatchNorm in the fusion blocks
+    "dac_small_nocls_clstoken_bn": (dict(backbone_size="small", lora_type="dvlora", image_shape=(42, 56), disable_conv_head=True,
+                                         include_cls_token=False, use_cls_token=True, use_bn=True), (3, 3, 42, 56), 91, 92),
     "dac_base_dvlora": (dict(backbone_size="base", lora_type="dvlora", image_shape=(70, 56), disable_conv_head=True),
                         (2, 3, 70, 56), 77, 78),
 }
@@ -92,11 +95,15 @@ ENDODAC_VIDEO = {
 
 def endodac_oracle_cfg(kw):
     return weights.endodac_cfg(kw["backbone_size"], kw.get("lora_type", "lora"), kw.get("r", 4),
-                               kw.get("residual_block_indexes", []), kw.get("disable_conv_head", False))
+                               kw.get("residual_block_indexes", []), kw.get("disable_conv_head", False),
+                               kw.get("include_cls_token", True), kw.get("use_cls_token", False), kw.get("use_bn", False))
 
 
 def make_endodac(manifest):
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     for name, (kw, shape, wseed, fseed) in ENDODAC_CASES.items():
+        if only and name not in only:
+            continue
         cfg = endodac_oracle_cfg(kw)
         sd = weights.to_endodac_keys(weights.make_state_dict(cfg, wseed))
         model = ref_import.build_reference_endodac(dict(kw, r=4))
@@ -116,6 +123,8 @@ def make_endodac(manifest):
             with open(os.path.join(GOLDEN_DIR, "state_dict_keys_%s.json" % name), "w") as f:
                 json.dump([[k, list(v.shape)] for k, v in model.state_dict().items()], f)
     for name, (kw, N, H, W, bs, wseed, fseed) in ENDODAC_VIDEO.items():
+        if only and name not in only:
+            continue
         cfg = endodac_oracle_cfg(kw)
         sd = weights.to_endodac_keys(weights.make_state_dict(cfg, wseed))
         model = ref_import.build_reference_endodac(dict(kw, r=4))

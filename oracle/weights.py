@@ -235,12 +235,14 @@ ENDODAC_SIZES = {  # models/endodac/endodac.py:171-199
 }
 
 
-def endodac_cfg(backbone_size="small", lora_type="dvlora", r=4, residual_block_indexes=(), disable_conv_head=True):
+def endodac_cfg(backbone_size="small", lora_type="dvlora", r=4, residual_block_indexes=(), disable_conv_head=True,
+                include_cls_token=True, use_cls_token=False, use_bn=False):
     """Oracle cfg of the reference ``endodac`` constructor (models/endodac/endodac.py:153-231)."""
     c = dict(ENDODAC_SIZES[backbone_size])
     c.update(lora_type=lora_type if lora_type in ("lora", "dvlora") else "none", r=r,
              residual_block_indexes=list(residual_block_indexes), disable_conv_head=disable_conv_head,
-             temporal_lora=False, motion=False)
+             temporal_lora=False, motion=False, include_cls_token=bool(include_cls_token), use_clstoken=bool(use_cls_token),
+             use_bn=bool(use_bn))
     # endodac.forward calls get_intermediate_layers(x, 4, ...) (endodac.py:254): an int n means the LAST
     # n blocks (vision_transformer.py:292-293), not the [2,5,8,11] table the class also defines (:183-186)
     depth = ENCODERS[c["encoder"]]["depth"]

@@ -19,7 +19,8 @@ DAC = [k for k, v in manifest().items() if v["kind"] == "endodac_forward"]
 
 def dac_cfg(ctor):
     return weights.endodac_cfg(ctor["backbone_size"], ctor.get("lora_type", "lora"), 4,
-                               ctor.get("residual_block_indexes", []), ctor.get("disable_conv_head", False))
+                               ctor.get("residual_block_indexes", []), ctor.get("disable_conv_head", False),
+                               ctor.get("include_cls_token", True), ctor.get("use_cls_token", False), ctor.get("use_bn", False))
 
 
 def dac_input(m):
