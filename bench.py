@@ -538,6 +538,21 @@ def main():
                         peak_source=peaks["source"] + (", burst bf16 (frac_of_sustained beside it)" if top["bound"] == "tensor" else ""))
         # whole-forward tensor utilisation: all contraction FLOPs / step time
         roofline["step_tflops"] = sum(r["flops"] for r in table) / K / (ms / K * 1e-3) / 1e12
+        if top["name"] == "flash_attention_tc":
+            # The kernel's real limiter: every score costs one MUFU ex2, 16 per clock per SM, against
+            # 2 x 64 MACs of tensor work -- at head dim 64 the exponentials need twice the cycles of the MMAs.  Stated beside the
+            # contract's tensor roofline so that the fraction can be read against the pipe that actually bounds the kernel.
+            h_, w_ = ctor["image_shape"]
+            S = (h_ // 14) * (w_ // 14) + 1
+            heads = {"vits": 6, "vitb": 12, "vitl": 16}[ctor["encoder"]]
+            blk = (S + 127) // 128 * 128
+            exps = float(B * T * heads) * blk * blk
+            mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak = 16.0 * 148 * mhz * 1e6
+            roofline["mufu"] = dict(exp_per_launch=exps, peak_exp_per_s=peak, achieved_exp_per_s=exps / (top["avg_us"] * 1e-6),
+                                    frac=exps / (top["avg_us"] * 1e-6) / peak,
+                                    note="ex2 on the MUFU pipe: 16 / clock / SM x 148 SMs at the sampled SM clock; the softmax instruction mix "
+                                         "reaches at most 86 % of it with two warps per scheduler (profiles/r2_microbench_softmax_mix.txt)")
     if args.kernels_out:
         with open(args.kernels_out, "w") as f:
             json.dump(dict(workload=args.workload, steps=K, profiled_ms_per_step=prof_ms / K, ms_per_step=ms / K, kernels=table), f, indent=1)

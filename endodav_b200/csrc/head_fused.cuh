@@ -18,7 +18,9 @@
 // Measured (round 2): staging the <= 20 x 12 source pixels of a tile in shared memory first (cp.async, double
 // buffered) and interpolating from there is SLOWER (615 vs 531 us at 32 x 296^2 -> 518^2): the ~9x re-fetch of source
 // pixels through L1/L2 is not what bounds the kernel; the producers' instruction stream is (ncu: 250 M instructions,
-// issue slots 45 % busy with only 8 producer warps, top stall long_scoreboard).
+// issue slots 45 % busy with only 8 producer warps, top stall long_scoreboard).  A software pipeline over the producers'
+// load batches (the next tile's 12 loads issued before the current batch is interpolated, two register sets) is slower too
+// (601 us): the 4-deep halo ring already lets the producers run ahead of the MMAs, the extra registers spill.
 #pragma once
 #include "tc_common.cuh"
 
