@@ -19,6 +19,7 @@ What is folded at pack time (all exact in real arithmetic, done in float64):
 Conv weights go to (out, ky, kx, c) order with channels padded to multiples of 64.
 """
 import math
+import os
 
 import torch
 
@@ -51,7 +52,11 @@ def merged_linear_weight(sd, prefix, lora_type, lora_scale=2.0):
     if lora_type == "dash":
         out = w + 2.0 * (B @ A)
         key = prefix + ".weight_u_top"
-        if key in sd:
+        # The reference keeps its call counter FLAG outside the state_dict: a freshly loaded dash checkpoint omits this term
+        # for its first 100 forwards (warm-up) and then RECOMPUTES U_top / Vt_top by SVD (mylora/layers.py:560-582).  The
+        # drop-in evaluates the post-warm-up form with the checkpoint's own U_top / Vt_top (what training converged to);
+        # ENDODAV_DASH_PHASE=warmup reproduces the reference's first 100 calls instead.
+        if key in sd and os.environ.get("ENDODAV_DASH_PHASE", "post").lower() != "warmup":
             out = out + sd[key].double() @ torch.diag(sd[prefix + ".lora_index"].double()) @ sd[prefix + ".weight_vt_top"].double()
         return out
     raise ValueError("unknown lora_type %r" % (lora_type,))
