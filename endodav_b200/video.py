@@ -155,12 +155,14 @@ class _Stager:
         from concurrent.futures import ThreadPoolExecutor
 
         self.frames, self.n, self.mine, self.WB = frames, n_frames, mine, WB
-        self.bufs = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8, pin_memory=True) for _ in range(self.RING)]
+        pin = torch.cuda.is_available()   # (the CPU unit test of the staging logic runs without CUDA)
+        self.bufs = [torch.empty(WB * INFER_LEN, H, W, 3, dtype=torch.uint8, pin_memory=pin) for _ in range(self.RING)]
         self.h2d_done = [None] * self.RING
         self.pool = ThreadPoolExecutor(max_workers=max(1, min(4, WB)))
         import weakref
         weakref.finalize(self, self.pool.shutdown, False)   # the worker threads go away with the stager
         self.tasks = {}          # (j, nb) -> (slot, futures)
+        self.slot_futs = [[] for _ in range(self.RING)]   # fill tasks last submitted per buffer (possibly never fetched)
         self.count = 0
 
     def _fill(self, slot, b, k, ev):
@@ -181,7 +183,11 @@ class _Stager:
         slot = self.count % self.RING
         self.count += 1
         ev, self.h2d_done[slot] = self.h2d_done[slot], None
-        self.tasks[(j, nb)] = (slot, [self.pool.submit(self._fill, slot, b, self.mine[j + b], ev) for b in range(nb)])
+        for f in self.slot_futs[slot]:
+            f.result()           # a prefetch that was never fetched (non-sequential caller) must not still be writing this buffer
+        futs = [self.pool.submit(self._fill, slot, b, self.mine[j + b], ev) for b in range(nb)]
+        self.slot_futs[slot] = futs
+        self.tasks[(j, nb)] = (slot, futs)
 
     def fetch(self, j, nb):
         """-> (slot, pinned uint8 [nb*32,H,W,3]) for windows mine[j:j+nb]; stages the next two batches of a sequential
