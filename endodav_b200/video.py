@@ -183,6 +183,7 @@ class _Stager:
         slot = self.count % self.RING
         self.count += 1
         ev, self.h2d_done[slot] = self.h2d_done[slot], None
+        self.tasks = {k: v for k, v in self.tasks.items() if v[0] != slot}   # a stale prefetch in this buffer is forgotten
         for f in self.slot_futs[slot]:
             f.result()           # a prefetch that was never fetched (non-sequential caller) must not still be writing this buffer
         futs = [self.pool.submit(self._fill, slot, b, self.mine[j + b], ev) for b in range(nb)]

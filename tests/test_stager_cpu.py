@@ -46,7 +46,7 @@ def test_stager_out_of_order_request_is_still_correct():
     frames = np.random.default_rng(1).integers(0, 256, size=(120, 4, 4, 3), dtype=np.uint8)
     mine = V.shard_windows(V.num_windows(120), 0, 1)
     st = V._Stager(frames, 120, mine, 2, 4, 4)
-    for j, nb in ((0, 2), (3, 1), (1, 2)):
+    for j, nb in ((0, 2), (3, 1), (1, 2), (2, 2), (4, 1), (0, 1), (4, 2), (2, 2)):
         slot, buf = st.fetch(j, nb)
         want = np.concatenate([frames[V.window_frame_indices(mine[j + b], 120)] for b in range(nb)])
         assert np.array_equal(buf.numpy(), want)
