@@ -88,7 +88,7 @@ struct edv_ctx {
   int debug = 0;
   int Kp = 640;
   // CUDA-graph replay of the planned forward (EDV_GRAPH=0 disables): up to GRAPH_SLOTS pointer sets per plan
-  static constexpr int GRAPH_SLOTS = 8;
+  static constexpr int GRAPH_SLOTS = 32;
   int graph_mode = 1;
   bool plan_warm = false;              // the first forward of a plan runs eagerly (one-time cudaFuncSetAttribute etc.)
   unsigned long long graph_clock = 0;

@@ -112,7 +112,7 @@ int edv_output_shape(const edv_ctx* ctx, int scale, int* h, int* w);
  * cudaGraphExec keyed by the external pointers of the call (frames, disp[], resized, workspace) and replays it on
  * later calls with the same pointers: no tensor-map encoding and one host launch instead of ~190 -- what the
  * reference's production resolution (224x280, evaluate_depth_video.py:86) needs, where the forward is launch bound.
- * A pointer set is captured the second time it is seen (callers whose buffers never repeat stay eager); up to 8 are
+ * A pointer set is captured the second time it is seen (callers whose buffers never repeat stay eager); up to 32 are
  * cached per plan (LRU); edv_plan, edv_set_weight (new pointer) and edv_set_debug drop them;
  * profiling (edv_profile) and debug taps run eagerly.  Default on (environment EDV_GRAPH=0 turns it off). */
 int edv_set_graph_mode(edv_ctx* ctx, int on);
