@@ -109,12 +109,14 @@ int edv_forward_u8(edv_ctx* ctx, const uint8_t* frames_dev, float* const disp_de
 int edv_output_shape(const edv_ctx* ctx, int scale, int* h, int* w);
 
 /* CUDA-graph replay.  After the first (eager) forward of a plan, edv_forward captures its launch sequence into a
- * cudaGraphExec keyed by the external pointers of the call (frames, disp[], resized, workspace) and replays it on
- * later calls with the same pointers: no tensor-map encoding and one host launch instead of ~190 -- what the
- * reference's production resolution (224x280, evaluate_depth_video.py:86) needs, where the forward is launch bound.
- * A pointer set is captured the second time it is seen (callers whose buffers never repeat stay eager); up to 32 are
- * cached per plan (LRU); edv_plan, edv_set_weight (new pointer) and edv_set_debug drop them;
- * profiling (edv_profile) and debug taps run eagerly.  Default on (environment EDV_GRAPH=0 turns it off). */
+ * cudaGraphExec keyed by the external INPUT pointers of the call (frames, resized, workspace) and replays it on later
+ * calls with the same pointers: no tensor-map encoding and one host launch instead of ~170 -- what the reference's
+ * production resolution (224x280, evaluate_depth_video.py:86) needs, where the forward is launch bound.  The disparity
+ * pyramid is produced in the plan's own buffers inside the graph and copied to disp[] behind the replay, so callers
+ * whose OUTPUT tensors are fresh on every call (any PyTorch caller) still replay.  A pointer set is captured the second
+ * time it is seen (callers whose input buffers never repeat stay eager); up to 32 are cached per plan (LRU); edv_plan,
+ * edv_set_weight (new pointer) and edv_set_debug drop them; profiling (edv_profile) and debug taps run eagerly.
+ * Default on (environment EDV_GRAPH=0 turns it off). */
 int edv_set_graph_mode(edv_ctx* ctx, int on);
 int edv_graph_count(const edv_ctx* ctx);
 /* "ok" after a successful capture, otherwise why the last attempt fell back to eager launches (never NULL). */
