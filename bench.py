@@ -481,16 +481,17 @@ def main():
     if not args.no_extras and args.workload == "vits_518_t32":
         if rank == 0:
             other = "bf16" if args.dtype != "bf16" else "fp16"
-            extra[other] = time_forward(E, synthetic, "vits_518_t32", other, dev, max(3, K // 3), 3)
+            jobs = [(other, lambda: time_forward(E, synthetic, "vits_518_t32", other, dev, max(3, K // 3), 3))]
             if world == 1:
-                extra["config1_vits_224x280_t8"] = time_forward(E, synthetic, "vits_224x280_t8", args.dtype, dev, 50, 10)
-                extra["vits_224x280_t32"] = time_forward(E, synthetic, "vits_224x280_t32", args.dtype, dev, 50, 10)
-                for name, fn in (("config4_vitl_518_t32_b4", lambda: time_forward(E, synthetic, "vitl_518_t32_b4", args.dtype, dev, 3, 3)),
-                                 ("config5_sweep", lambda: time_config5_sweep(E, synthetic, args.dtype, dev))):
-                    try:
-                        extra[name] = fn()
-                    except Exception as exc:  # the headline line must survive a failure of an extra
-                        extra[name] = dict(error=repr(exc)[:300])
+                jobs += [("config1_vits_224x280_t8", lambda: time_forward(E, synthetic, "vits_224x280_t8", args.dtype, dev, 50, 10)),
+                         ("vits_224x280_t32", lambda: time_forward(E, synthetic, "vits_224x280_t32", args.dtype, dev, 50, 10)),
+                         ("config4_vitl_518_t32_b4", lambda: time_forward(E, synthetic, "vitl_518_t32_b4", args.dtype, dev, 3, 3)),
+                         ("config5_sweep", lambda: time_config5_sweep(E, synthetic, args.dtype, dev))]
+            for name, fn in jobs:
+                try:
+                    extra[name] = fn()
+                except Exception as exc:  # the headline line must survive a failure of an extra
+                    extra[name] = dict(error=repr(exc)[:300])
         if world > 1:
             dist.barrier()
         try:
