@@ -152,13 +152,19 @@ __global__ void __launch_bounds__(GB_THREADS, 1) gemm_bres_kernel(const __grid_c
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();     // PDL: everything above ran under the previous kernel's tail; its results are visible from here
+  // PDL: everything above ran under the previous kernel's tail; its results are visible after pdl_wait().  The producer
+  // first issues the loads of its resident W tile -- weights are never written inside a forward -- so that up to 144 KB
+  // of L2 -> shared-memory traffic also travels under the previous kernel's tail.
+  if (warp != 0) pdl_wait();
   if (tm_ && threadIdx.x == 0) tm_[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(b_full, (uint32_t)kblocks * B_KB_BYTES);
       for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sB + (size_t)kb * B_KB_BYTES, &tmB, b_full, kb * 64, tile_n * BN);
+    }
+    pdl_wait();
+    if (lane == 0) {
       uint32_t kc = 0;
       int ti = 0;
       // L2 prefetch distance: GB_PF_TILES m-tiles of A ahead of the shared-memory ring (tc_common.cuh tma_prefetch_2d)
