@@ -223,7 +223,7 @@ __device__ __forceinline__ void gt_epilogue(const Epi& e, uint32_t trow, bool va
   const int o32 = valid ? (int)orow_lin : -1;
   const int j = lane & 7, rsub = lane >> 3;
   // the two warpgroups of an accumulator split its columns: [0, BN/2) and [BN/2, BN)
-  constexpr int CH0 = (BN >= 64) ? BN / 2 : BN;
+  [[maybe_unused]] constexpr int CH0 = (BN >= 64) ? BN / 2 : BN;
   if (e.act == ACT_HEAD) {
     // whole row in one tile (BN == N == 32): relu(conv+b) . w + b -> relu  (dpt.py:118-123)
     if (half != 0) return;
